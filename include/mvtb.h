@@ -1,0 +1,120 @@
+/* mvtb.h — C ABI of libmvtb.so: B200 (sm_100a) kernels for the MRI artifact transforms of
+ * yanielc/medical-vision-textural-bias.
+ *
+ * The reference is pure Python and has no FFI of its own; these entry points are what a
+ * binding for its hot path (source_code/filters_and_operators.py = F, stylization_layers.py = S)
+ * calls.  Each entry cites the reference routine whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 (MVTB_OK) on success, a negative MVTB_E* code for argument
+ *     errors, or a positive cudaError_t; nothing throws, nothing calls exit();
+ *   - all work is enqueued asynchronously on the caller's stream (`stream` is a cudaStream_t
+ *     passed as void*); only plan_create/plan_destroy may synchronise;
+ *   - the caller owns every in/out/u/minmax device buffer; the plan owns its tables and
+ *     workspace; a plan is used from one stream at a time;
+ *   - tensors are contiguous row-major fp32; a "volume" is one block of the last `ndim_fft`
+ *     axes (the unit the reference FFTs), e.g. one channel of a (C,H,W,D) sample for the
+ *     3-D transforms, or one batch item (C,H,W,D) for the 4-D FFT of GibbsNoiseLayer.
+ */
+#ifndef MVTB_H
+#define MVTB_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVTB_VERSION 100
+
+#define MVTB_OK 0
+#define MVTB_EINVAL (-1)        /* bad argument (null pointer, non-positive size, ...) */
+#define MVTB_EUNSUPPORTED (-2)  /* shape / option outside what the kernels implement */
+#define MVTB_ENOMEM (-3)
+#define MVTB_ENODEVICE (-4)     /* no usable CUDA device: there is no CPU fallback */
+
+#define MVTB_MAX_FFT_DIMS 4
+#define MVTB_MAX_SPIKES 8
+
+/* mask_kind */
+#define MVTB_MASK_NONE 0
+/* keep  <=>  sum_d (i_d - floor(N_d/2))^2 <= mask_thresh   (disk_mask, F:165-197; the fp32
+ * comparison `< r**2` is turned into this integer threshold on the host) */
+#define MVTB_MASK_DISK 1
+/* keep  <=>  sum_d (2 i_d - (N_d-1))^2 <= mask_thresh   (GibbsNoise F:686-698 and
+ * GibbsNoiseLayer S:99-109; i_d = fftshift-ed index; threshold found on the host by evaluating
+ * the reference's own fp64 / fp32 predicate, which is monotone in the sum) */
+#define MVTB_MASK_CENTRED 2
+
+typedef struct mvtb_spike {
+    int32_t idx[MVTB_MAX_FFT_DIMS]; /* fftshift-ed k-space index per FFT axis, outermost first
+                                       (what the reference writes to: F:387, F:975-983) */
+    float amplitude;                /* exp(log-intensity) in fp32 (F:389, F:942) */
+    int32_t reserved;
+} mvtb_spike;
+
+/* One fused k-space pass:  out = Re ifftn( W * ( M * fftn(x) with spikes set ) )
+ * = RandFourierDiskMaskd (F:236-252) / GibbsNoise (F:663-705) / GibbsNoiseLayer (S:79-116)
+ *   -> RandPlaneWaves_ellipsoid (F:370-393) / KSpaceSpikeNoise (F:906-945)
+ *   -> WrapArtifact (F:503-515), each stage optional, in that order. */
+typedef struct mvtb_chain_desc {
+    int32_t mask_kind;
+    int32_t mask_ndim;     /* number of trailing axes in the distance (<= ndim_fft) */
+    int64_t mask_thresh;   /* integer threshold; negative keeps nothing */
+    int32_t inside_off;    /* 1: mask = 1 - mask (F:194-195) */
+    int32_t n_spikes;      /* 0..MVTB_MAX_SPIKES, distinct locations */
+    float wrap_alpha;      /* weight of odd fftshift-ed indices (F:509-511) */
+    int32_t wrap_naxes;    /* 0 = no wrap; else the trailing wrap_naxes axes are weighted (3 in the reference) */
+    mvtb_spike spikes[MVTB_MAX_SPIKES];
+} mvtb_chain_desc;
+
+typedef struct mvtb_plan mvtb_plan;
+
+int mvtb_version(void);
+/* copies the calling thread's last error text; returns its length */
+int mvtb_last_error(char* buf, int n);
+
+/* FFT plan over the last ndim_fft (2..4) axes, fft_shape outermost first.  chunk_volumes =
+ * how many volumes are in flight between kernels (workspace = chunk_volumes half-spectra).
+ * Every axis length must factor into primes <= 31 (240, 155, 128, 64, ... do). */
+int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_shape, int chunk_volumes, int device);
+int mvtb_plan_destroy(mvtb_plan* plan);
+size_t mvtb_plan_workspace_bytes(const mvtb_plan* plan);
+
+/* Fused chain over n_volumes volumes.  desc: host array of n_desc entries, n_desc == 1
+ * (shared) or n_volumes.  minmax_out (nullable): device float[2*n_samples], receives
+ * (min, max) of `out` per sample, a sample being vols_per_sample consecutive volumes
+ * (what SaltAndPepper's x.min()/x.max() needs, F:476).  in == out is allowed. */
+int mvtb_kspace_chain_f32(mvtb_plan* plan, const float* in, float* out, int n_volumes,
+                          const mvtb_chain_desc* desc, int n_desc,
+                          float* minmax_out, int vols_per_sample, void* stream);
+
+/* sum over the full (unshifted, unnormalised) spectrum of log(|k| + 1e-10) per volume, into
+ * device double[n_volumes]; the caller divides by the volume size and multiplies by 2.5
+ * (KSpaceSpikeNoise default intensity F:932-933, RandKSpaceSpikeNoise default range F:1127-1130). */
+int mvtb_kspace_logabs_sum_f32(mvtb_plan* plan, const float* in, int n_volumes, double* sums_out, void* stream);
+
+/* (min, max) per sample of n_per_sample contiguous floats -> device float[2*n_samples] (F:476) */
+int mvtb_minmax_f32(const float* in, size_t n_per_sample, int n_samples, float* minmax_out, void* stream);
+
+/* SaltAndPepper.salt_and_pepper (F:465-482): y = u <= p/2 ? min/2 : (u <= p ? max/2 : x), with
+ * (min,max) per sample read from minmax (device, from mvtb_minmax_f32 or the chain).
+ * u: device uniforms of the same shape (bit-exact parity with the reference given its mask),
+ * or NULL -> counter-based Philox4x32-10 keyed by `seed`, element i of the whole buffer uses
+ * counter (offset + i/4), lane i%4.  in == out allowed. */
+int mvtb_salt_pepper_f32(const float* in, float* out, size_t n_per_sample, int n_samples,
+                         const float* u, uint64_t seed, uint64_t offset, float p,
+                         const float* minmax, void* stream);
+
+/* the uniforms mvtb_salt_pepper_f32 uses when u == NULL (for tests and for feeding the oracle) */
+int mvtb_philox_uniform_f32(float* out, size_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* WrapArtifact (F:503-515) on (C,H,W,D) when H, W and D are all even: the image-domain fold
+ * out = prod_axes (c0 + s c1 Roll_{N/2}) x, c0=(1+alpha)/2, c1=(1-alpha)/2, s=(-1)^(N/2)
+ * (SURVEY A.3).  Returns MVTB_EUNSUPPORTED for an odd axis (use the chain). in != out. */
+int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W, int D, float alpha, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVTB_H */

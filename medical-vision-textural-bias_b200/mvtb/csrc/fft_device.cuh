@@ -1,0 +1,191 @@
+// fft_device.cuh — batched in-place mixed-radix FFT stages on shared memory.
+//
+// Forward = decimation in frequency: natural order in, mixed-radix digit-reversed order out
+// (position p holds bin pos2k[p]).  Inverse = decimation in time over the same positions:
+// digit-reversed in, natural out.  Nothing is ever permuted: the k-space pointwise stage
+// looks frequencies up through pos2k, so forward -> pointwise -> inverse needs no transpose,
+// no ping-pong buffer and no fftshift (the reference's fftshift/ifftshift copies,
+// F:270-279, are index arithmetic here).
+//
+// A stage with radix R over blocks of length L (sub-length m = L/R):
+//   fwd:  v_q = sum_p x[j + p m] w_R^{pq};  x[j + q m] = v_q * w_L^{jq}
+//   inv:  v_q = x[j + q m] * conj(w_L^{jq});  x[j + p m] = sum_q v_q conj(w_R^{pq})
+// w_L^{jq} = tw[j q (n/L)] with j q < L, so the table index never wraps.
+#pragma once
+#include "mvtb_common.cuh"
+
+namespace mvtb {
+
+template <int R, bool INV>
+struct Butterfly;
+
+template <bool INV>
+struct Butterfly<2, INV> {
+    static __device__ __forceinline__ void run(cf* v, const cf*, int) {
+        cf a = v[0], b = v[1];
+        v[0] = cadd(a, b);
+        v[1] = csub(a, b);
+    }
+};
+
+template <bool INV>
+struct Butterfly<4, INV> {
+    static __device__ __forceinline__ void run(cf* v, const cf*, int) {
+        cf s02 = cadd(v[0], v[2]), d02 = csub(v[0], v[2]);
+        cf s13 = cadd(v[1], v[3]), d13 = csub(v[1], v[3]);
+        cf r = INV ? cmuli(d13) : cmulni(d13);   // (+-i)(x1 - x3)
+        v[0] = cadd(s02, s13);
+        v[1] = cadd(d02, r);
+        v[2] = csub(s02, s13);
+        v[3] = csub(d02, r);
+    }
+};
+
+template <bool INV>
+struct Butterfly<3, INV> {
+    static __device__ __forceinline__ void run(cf* v, const cf*, int) {
+        const float S = 0.86602540378443864676f;
+        cf bc = cadd(v[1], v[2]);
+        cf t = cmk(v[0].x - 0.5f * bc.x, v[0].y - 0.5f * bc.y);
+        cf s = cscale(csub(v[1], v[2]), S);
+        cf r = INV ? cmuli(s) : cmulni(s);
+        v[0] = cadd(v[0], bc);
+        v[1] = cadd(t, r);
+        v[2] = csub(t, r);
+    }
+};
+
+template <bool INV>
+struct Butterfly<5, INV> {
+    static __device__ __forceinline__ void run(cf* v, const cf*, int) {
+        const float C1 = 0.30901699437494742410f, C2 = -0.80901699437494742410f;
+        const float S1 = 0.95105651629515357212f, S2 = 0.58778525229247312917f;
+        cf t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+        cf t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+        cf a = v[0];
+        cf m1 = cmk(a.x + C1 * t1.x + C2 * t2.x, a.y + C1 * t1.y + C2 * t2.y);
+        cf m2 = cmk(a.x + C2 * t1.x + C1 * t2.x, a.y + C2 * t1.y + C1 * t2.y);
+        cf n1 = cmk(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y);
+        cf n2 = cmk(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y);
+        cf r1 = INV ? cmuli(n1) : cmulni(n1);
+        cf r2 = INV ? cmuli(n2) : cmulni(n2);
+        v[0] = cadd(a, cadd(t1, t2));
+        v[1] = cadd(m1, r1);
+        v[4] = csub(m1, r1);
+        v[2] = cadd(m2, r2);
+        v[3] = csub(m2, r2);
+    }
+};
+
+// Odd prime P >= 7 by the symmetric direct DFT:
+//   y_q, y_{P-q} = A_q -+ i B_q,  A_q = x0 + sum_k (x_k + x_{P-k}) cos(2 pi kq/P),
+//                                 B_q = sum_k (x_k - x_{P-k}) sin(2 pi kq/P),  k = 1..(P-1)/2
+// roots come from the axis table: w_P^t = tw[t * (n/P)] = (cos, -sin).
+template <int P, bool INV>
+struct Butterfly {
+    static __device__ __forceinline__ void run(cf* v, const cf* tw, int rstep) {
+        constexpr int H = (P - 1) / 2;
+        cf sm[H], df[H];
+        cf x0 = v[0], tot = v[0];
+        MVTB_UNROLL
+        for (int k = 0; k < H; ++k) {
+            sm[k] = cadd(v[k + 1], v[P - 1 - k]);
+            df[k] = csub(v[k + 1], v[P - 1 - k]);
+            tot = cadd(tot, sm[k]);
+        }
+        v[0] = tot;
+        MVTB_UNROLL
+        for (int q = 1; q <= H; ++q) {
+            cf A = x0, B = cmk(0.f, 0.f);
+            MVTB_UNROLL
+            for (int k = 1; k <= H; ++k) {
+                cf w = __ldg(tw + ((k * q) % P) * rstep);   // (cos, -sin)
+                A.x += sm[k - 1].x * w.x;
+                A.y += sm[k - 1].y * w.x;
+                B.x -= df[k - 1].x * w.y;
+                B.y -= df[k - 1].y * w.y;
+            }
+            cf r = INV ? cmuli(B) : cmulni(B);
+            v[q] = cadd(A, r);
+            v[P - q] = csub(A, r);
+        }
+    }
+};
+
+// One radix-R stage over `count` sequences living in shared memory.
+// element (seq s, index j) is at  base[s * seq_stride + j * elem_stride].
+// Tasks are (sequence, butterfly); SEQ_FAST picks which one is fastest across threads.
+template <int R, bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_stride, int count,
+                                          int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    const int m = L / R;
+    const int per_seq = n / R;
+    const int total = per_seq * count;
+    const int tstep = n / L;
+    const int rstep = n / R;
+    for (int task = tid; task < total; task += nthr) {
+        int sq, b;
+        if (SEQ_FAST) { sq = task % count; b = task / count; }
+        else          { b = task % per_seq; sq = task / per_seq; }
+        const int blk = b / m, j = b - blk * m;
+        cf* p = base + (size_t)sq * seq_stride + (size_t)(blk * L + j) * elem_stride;
+        const int es = m * elem_stride;
+        cf v[R];
+        MVTB_UNROLL
+        for (int q = 0; q < R; ++q) v[q] = p[q * es];
+        if (INV) {
+            if (j != 0) {
+                MVTB_UNROLL
+                for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * tstep));
+            }
+            Butterfly<R, true>::run(v, tw, rstep);
+        } else {
+            Butterfly<R, false>::run(v, tw, rstep);
+            if (j != 0) {
+                MVTB_UNROLL
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + j * q * tstep));
+            }
+        }
+        MVTB_UNROLL
+        for (int q = 0; q < R; ++q) p[q * es] = v[q];
+    }
+}
+
+template <bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stride, int elem_stride, int count,
+                                                   int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    switch (R) {
+#define MVTB_CASE(RR) case RR: fft_stage<RR, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
+        MVTB_CASE(2) MVTB_CASE(3) MVTB_CASE(4) MVTB_CASE(5) MVTB_CASE(7) MVTB_CASE(11) MVTB_CASE(13)
+        MVTB_CASE(17) MVTB_CASE(19) MVTB_CASE(23) MVTB_CASE(29) MVTB_CASE(31)
+#undef MVTB_CASE
+        default: break;
+    }
+}
+
+// Whole transform; the caller has synchronised before, and a __syncthreads() follows every stage.
+template <bool SEQ_FAST>
+__device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
+                                            int tid, int nthr) {
+    int L = ax.n;
+    for (int s = 0; s < ax.nstage; ++s) {
+        const int R = ax.radix[s];
+        fft_stage_dispatch<false, SEQ_FAST>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        L /= R;
+        __syncthreads();
+    }
+}
+
+template <bool SEQ_FAST>
+__device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
+                                            int tid, int nthr) {
+    int L = 1;
+    for (int s = ax.nstage - 1; s >= 0; --s) {
+        const int R = ax.radix[s];
+        L *= R;
+        fft_stage_dispatch<true, SEQ_FAST>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        __syncthreads();
+    }
+}
+
+}  // namespace mvtb

@@ -1,0 +1,516 @@
+// kspace_chain.cu — general fused k-space chain:  out = Re ifftn( W * (M * fftn(x) + spikes) ).
+//
+// Replaces, in one forward + one inverse transform and with no fftshift copies, complex
+// temporaries or materialised masks:
+//   RandFourierDiskMaskd.__call__ (F:236-252)   GibbsNoise.__call__ (F:663-705)
+//   GibbsNoiseLayer.forward (S:79-116)          RandPlaneWaves_ellipsoid.__call__ (F:370-393)
+//   KSpaceSpikeNoise.__call__ (F:906-945)       WrapArtifact.__call__ (F:503-515)
+// (F = source_code/filters_and_operators.py, S = source_code/stylization_layers.py.)
+//
+// Pipeline per chunk of volumes (half-spectrum workspace, last axis R2C by the
+// "two real rows = one complex FFT" trick, valid for odd lengths such as 155):
+//   k_rows_fwd            real rows -> half-spectrum rows (axis 0)
+//   k_axis<FWD>           middle axes, in place, digit-reversed order kept
+//   k_axis<MID>           outermost axis: forward, pointwise (mask / spike / wrap / 1/N), inverse
+//   k_axis<INV>           middle axes back
+//   k_rows_inv            half-spectrum rows -> real rows, fused per-sample min/max
+#include <math.h>
+#include <string.h>
+
+#include "fft_device.cuh"
+
+namespace mvtb {
+
+enum { AX_FWD = 0, AX_INV = 1, AX_MID = 2, AX_STATS = 3 };
+static const int kThreads = 256;
+
+struct ChainGeom {
+    int ndim;
+    int shape[MVTB_MAX_FFT_DIMS];         // axis 0 = last axis
+    int nh;
+    const int* pos2k[MVTB_MAX_FFT_DIMS];
+    float scale;                          // 1 / prod(shape)
+};
+
+// ------------------------------------------------------------------ float atomics on (min,max)
+__device__ __forceinline__ void atomic_min_f32(float* addr, float v) {
+    v += 0.0f;   // -0 -> +0
+    if (v >= 0.f) atomicMin((int*)addr, __float_as_int(v));
+    else atomicMax((unsigned*)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f32(float* addr, float v) {
+    v += 0.0f;
+    if (v >= 0.f) atomicMax((int*)addr, __float_as_int(v));
+    else atomicMin((unsigned*)addr, __float_as_uint(v));
+}
+
+__global__ void k_minmax_init(float* mm, int n_samples) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_samples) {
+        mm[2 * i] = __int_as_float(0x7f800000);
+        mm[2 * i + 1] = __int_as_float((int)0xff800000u);
+    }
+}
+
+// block-wide (min,max) -> one atomic pair; every thread of the block must call it
+__device__ __forceinline__ void block_minmax_commit(float lo, float hi, float* mm) {
+    __shared__ float s_lo[32], s_hi[32];
+    MVTB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_lo[w] = lo; s_hi[w] = hi; }
+    __syncthreads();
+    if (w == 0) {
+        lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+        hi = lane < nw ? s_hi[lane] : __int_as_float((int)0xff800000u);
+        MVTB_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { atomic_min_f32(mm, lo); atomic_max_f32(mm + 1, hi); }
+    }
+}
+
+// ------------------------------------------------------------------ axis 0: real rows <-> half spectrum
+__global__ void __launch_bounds__(256)
+k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh, int pitch,
+           int pairs_per_cta, long long n_rows) {
+    MVTB_DYN_SMEM(smem_raw);
+    cf* s = (cf*)smem_raw;
+    const int n = ax.n, tid = threadIdx.x, nthr = blockDim.x;
+    const long long n_pairs = (n_rows + 1) >> 1;
+    const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
+    long long rem = n_pairs - pair0;
+    const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
+
+    for (int e = tid; e < np * n; e += nthr) {
+        const int rp = e / n, j = e - rp * n;
+        const long long ra = 2 * (pair0 + rp);
+        const float a = in[ra * n + j];
+        const float b = (ra + 1 < n_rows) ? in[(ra + 1) * n + j] : 0.f;
+        s[rp * pitch + j] = cmk(a, b);
+    }
+    __syncthreads();
+    fft_forward<false>(ax, s, pitch, 1, np, tid, nthr);
+
+    // Z = FFT(a + i b):  A[k] = (Z[k] + conj Z[n-k]) / 2,  B[k] = (Z[k] - conj Z[n-k]) / (2i)
+    for (int e = tid; e < np * nh; e += nthr) {
+        const int rp = e / nh, k = e - rp * nh;
+        const int kn = k == 0 ? 0 : n - k;
+        const cf zk = s[rp * pitch + __ldg(ax.k2pos + k)];
+        const cf zn = s[rp * pitch + __ldg(ax.k2pos + kn)];
+        const long long ra = 2 * (pair0 + rp);
+        ws[ra * nh + k] = cmk(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        if (ra + 1 < n_rows) ws[(ra + 1) * nh + k] = cmk(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int nh, int pitch,
+           int pairs_per_cta, long long n_rows, float* __restrict__ minmax, long long rows_per_sample,
+           long long row_base) {
+    MVTB_DYN_SMEM(smem_raw);
+    cf* s = (cf*)smem_raw;
+    const int n = ax.n, tid = threadIdx.x, nthr = blockDim.x;
+    const long long n_pairs = (n_rows + 1) >> 1;
+    const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
+    long long rem = n_pairs - pair0;
+    const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
+
+    // Z[k] = A[k] + i B[k];  Z[n-k] = conj A[k] + i conj B[k]
+    for (int e = tid; e < np * nh; e += nthr) {
+        const int rp = e / nh, k = e - rp * nh;
+        const long long ra = 2 * (pair0 + rp);
+        const cf A = ws[ra * nh + k];
+        const cf B = (ra + 1 < n_rows) ? ws[(ra + 1) * nh + k] : cmk(0.f, 0.f);
+        s[rp * pitch + __ldg(ax.k2pos + k)] = cmk(A.x - B.y, A.y + B.x);
+        if (k != 0 && 2 * k != n) s[rp * pitch + __ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
+    }
+    __syncthreads();
+    fft_inverse<false>(ax, s, pitch, 1, np, tid, nthr);
+
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
+    const long long row_first = 2 * pair0;
+    long long row_last = row_first + 2 * np - 1;
+    if (row_last >= n_rows) row_last = n_rows - 1;
+    const bool want_mm = minmax != nullptr;
+    const bool uniform = want_mm && ((row_base + row_first) / rows_per_sample == (row_base + row_last) / rows_per_sample);
+    for (int e = tid; e < np * n; e += nthr) {
+        const int rp = e / n, j = e - rp * n;
+        const long long ra = 2 * (pair0 + rp);
+        const cf z = s[rp * pitch + j];
+        out[ra * n + j] = z.x;
+        const bool hasb = ra + 1 < n_rows;
+        if (hasb) out[(ra + 1) * n + j] = z.y;
+        if (want_mm) {
+            if (uniform) {
+                lo = fminf(lo, z.x); hi = fmaxf(hi, z.x);
+                if (hasb) { lo = fminf(lo, z.y); hi = fmaxf(hi, z.y); }
+            } else {
+                float* ma = minmax + 2 * ((row_base + ra) / rows_per_sample);
+                atomic_min_f32(ma, z.x); atomic_max_f32(ma + 1, z.x);
+                if (hasb) {
+                    float* mb = minmax + 2 * ((row_base + ra + 1) / rows_per_sample);
+                    atomic_min_f32(mb, z.y); atomic_max_f32(mb + 1, z.y);
+                }
+            }
+        }
+    }
+    if (uniform) block_minmax_commit(lo, hi, minmax + 2 * ((row_base + row_first) / rows_per_sample));
+}
+
+// ------------------------------------------------------------------ pointwise k-space stage
+__device__ __forceinline__ long long mask_term(int kind, int i, int n) {
+    const long long d = kind == MVTB_MASK_DISK ? (long long)(i - n / 2) : (long long)(2 * i - (n - 1));
+    return d * d;
+}
+
+__device__ __forceinline__ cf spike_value(cf ko, float amp) {
+    const float mag = hypotf(ko.x, ko.y);
+    if (mag > 0.f) return cmk(amp * (ko.x / mag), amp * (ko.y / mag));
+    return cmk(amp, 0.f);   // angle(0) = 0 (F:384, F:928)
+}
+
+// Axes >= 1 of the half-spectrum workspace, viewed as [outer][n][inner].
+// One CTA owns a tile of T adjacent `inner` columns over the whole axis: shared memory [n][T].
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int ntiles,
+       ChainGeom g, DescPack pack, double* __restrict__ sums) {
+    MVTB_DYN_SMEM(smem_raw);
+    cf* s = (cf*)smem_raw;
+    const int n = ax.n, tid = threadIdx.x, nthr = blockDim.x;
+    const long long o = blockIdx.x / ntiles;
+    const long long i0 = (long long)(blockIdx.x - o * ntiles) * T;
+    cf* base = ws + o * (long long)n * inner + i0;
+    const int t = tid % T;                 // nthr % T == 0: a thread always sees the same column
+    const bool col_ok = i0 + t < inner;
+
+    for (int e = tid; e < n * T; e += nthr) {
+        const int j = e / T;
+        s[e] = col_ok ? base[(long long)j * inner + t] : cmk(0.f, 0.f);
+    }
+    __syncthreads();
+
+    if (MODE != AX_INV) fft_forward<true>(ax, s, 1, T, T, tid, nthr);
+
+    if (MODE == AX_MID) {
+        const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
+        // ---- per-column part: axes below this one
+        int ish[MVTB_MAX_FFT_DIMS], ineg[MVTB_MAX_FFT_DIMS];
+        long long rest = i0 + t;
+        {
+            const int k0 = (int)(rest % g.nh);
+            rest /= g.nh;
+            ish[0] = (k0 + g.shape[0] / 2) % g.shape[0];
+        }
+        for (int b = 1; b < axis; ++b) {
+            const int p = (int)(rest % g.shape[b]);
+            rest /= g.shape[b];
+            ish[b] = (__ldg(g.pos2k[b] + p) + g.shape[b] / 2) % g.shape[b];
+        }
+        long long qp = 0, qn = 0;
+        float wgt = g.scale;
+        unsigned mpos = 0, mneg = 0;       // per-spike "all lower axes match" bits
+        for (int b = 0; b < axis; ++b) {
+            const int nb = g.shape[b];
+            ineg[b] = (2 * (nb / 2) - ish[b] + nb) % nb;
+            if (d.mask_kind != MVTB_MASK_NONE && b < d.mask_ndim) {
+                qp += mask_term(d.mask_kind, ish[b], nb);
+                qn += mask_term(d.mask_kind, ineg[b], nb);
+            }
+            if (b < d.wrap_naxes && (ish[b] & 1)) wgt *= d.wrap_alpha;
+        }
+        for (int sI = 0; sI < d.n_spikes; ++sI) {
+            bool p = true, q = true;
+            for (int b = 0; b < axis; ++b) {
+                p = p && (ish[b] == d.sp[sI].idx[b]);
+                q = q && (ineg[b] == d.sp[sI].idx[b]);
+            }
+            mpos |= (p ? 1u : 0u) << sI;
+            mneg |= (q ? 1u : 0u) << sI;
+        }
+        // ---- per-bin part
+        if (col_ok) {
+            for (int j = tid / T; j < n; j += nthr / T) {
+                const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
+                const int imn = (2 * (n / 2) - im + n) % n;
+                float meff = 1.f;
+                if (d.mask_kind != MVTB_MASK_NONE) {
+                    long long a = qp, c = qn;
+                    if (axis < d.mask_ndim) { a += mask_term(d.mask_kind, im, n); c += mask_term(d.mask_kind, imn, n); }
+                    const int kp = (a <= d.thr ? 1 : 0) ^ d.inside_off;
+                    const int kn = (c <= d.thr ? 1 : 0) ^ d.inside_off;
+                    meff = 0.5f * (float)(kp + kn);
+                }
+                const cf K = s[j * T + t];
+                cf acc = cscale(K, meff);
+                if ((mpos | mneg) != 0u) {
+                    for (int sI = 0; sI < d.n_spikes; ++sI) {
+                        const bool isp = ((mpos >> sI) & 1u) && im == d.sp[sI].idx[axis];
+                        const bool isn = ((mneg >> sI) & 1u) && imn == d.sp[sI].idx[axis];
+                        if (!isp && !isn) continue;
+                        const float ms = (float)d.sp[sI].mask_at_spike;
+                        if (isp && isn) {                 // self-conjugate bin: Re(new)
+                            const cf ko = cscale(K, ms);
+                            const cf nw = spike_value(ko, d.sp[sI].amp);
+                            acc.x += nw.x - ko.x;
+                            acc.y -= ko.y;
+                        } else if (isp) {
+                            const cf ko = cscale(K, ms);
+                            const cf nw = spike_value(ko, d.sp[sI].amp);
+                            acc.x += 0.5f * (nw.x - ko.x);
+                            acc.y += 0.5f * (nw.y - ko.y);
+                        } else {                          // this bin is -f_s: K(f_s) = conj K here
+                            const cf ko = cscale(cconj(K), ms);
+                            const cf nw = spike_value(ko, d.sp[sI].amp);
+                            acc.x += 0.5f * (nw.x - ko.x);
+                            acc.y -= 0.5f * (nw.y - ko.y);
+                        }
+                    }
+                }
+                float w = wgt;
+                if (axis < d.wrap_naxes && (im & 1)) w *= d.wrap_alpha;
+                s[j * T + t] = cscale(acc, w);
+            }
+        }
+        __syncthreads();
+    }
+
+    if (MODE == AX_STATS) {
+        double acc = 0.0;
+        if (col_ok) {
+            const int k0 = (int)((i0 + t) % g.nh);
+            const bool self = k0 == 0 || (2 * k0 == g.shape[0]);
+            const double wt = self ? 1.0 : 2.0;
+            for (int j = tid / T; j < n; j += nthr / T) {
+                const cf K = s[j * T + t];
+                acc += wt * (double)logf(hypotf(K.x, K.y) + 1e-10f);
+            }
+        }
+        __shared__ double s_acc[32];
+        MVTB_UNROLL
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if ((tid & 31) == 0) s_acc[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (nthr + 31) / 32; ++w) tot += s_acc[w];
+            atomicAdd(sums + o, tot);
+        }
+        return;
+    }
+
+    if (MODE != AX_FWD) fft_inverse<true>(ax, s, 1, T, T, tid, nthr);
+
+    for (int e = tid; e < n * T; e += nthr) {
+        const int j = e / T;
+        if (col_ok) base[(long long)j * inner + t] = s[e];
+    }
+}
+
+// ------------------------------------------------------------------ host side
+int configure_chain_kernels(const mvtb_plan* p) {
+#ifndef MVTB_EMU
+    const int big = 227 * 1024;
+    MVTB_CUDA(cudaFuncSetAttribute(k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MVTB_CUDA(cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#endif
+    (void)p;
+    return MVTB_OK;
+}
+
+static ChainGeom make_geom(const mvtb_plan* p) {
+    ChainGeom g;
+    memset(&g, 0, sizeof(g));
+    g.ndim = p->ndim;
+    g.nh = p->nh;
+    double tot = 1.0;
+    for (int a = 0; a < p->ndim; ++a) {
+        g.shape[a] = p->shape[a];
+        g.pos2k[a] = p->ax[a].pos2k;
+        tot *= (double)p->shape[a];
+    }
+    g.scale = (float)(1.0 / tot);
+    return g;
+}
+
+// validates one user descriptor against the plan and converts it to the device view
+static int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
+    memset(d, 0, sizeof(*d));
+    if (u->mask_kind < MVTB_MASK_NONE || u->mask_kind > MVTB_MASK_CENTRED) { set_error("chain: mask_kind=%d", u->mask_kind); return MVTB_EINVAL; }
+    if (u->mask_kind != MVTB_MASK_NONE && (u->mask_ndim < 1 || u->mask_ndim > p->ndim)) { set_error("chain: mask_ndim=%d with ndim_fft=%d", u->mask_ndim, p->ndim); return MVTB_EINVAL; }
+    if (u->n_spikes < 0 || u->n_spikes > MVTB_MAX_SPIKES) { set_error("chain: n_spikes=%d (max %d)", u->n_spikes, MVTB_MAX_SPIKES); return MVTB_EUNSUPPORTED; }
+    if (u->wrap_naxes < 0 || u->wrap_naxes > p->ndim) { set_error("chain: wrap_naxes=%d", u->wrap_naxes); return MVTB_EINVAL; }
+    d->mask_kind = u->mask_kind;
+    d->mask_ndim = u->mask_kind == MVTB_MASK_NONE ? 0 : u->mask_ndim;
+    d->thr = u->mask_thresh;
+    d->inside_off = u->inside_off ? 1 : 0;
+    d->n_spikes = u->n_spikes;
+    d->wrap_alpha = u->wrap_alpha;
+    d->wrap_naxes = u->wrap_naxes;
+    for (int s = 0; s < u->n_spikes; ++s) {
+        long long q = 0;
+        for (int a = 0; a < p->ndim; ++a) {
+            const int idx = u->spikes[s].idx[p->ndim - 1 - a];     // user order: outermost first
+            const int n = p->shape[a];
+            if (idx < 0 || idx >= n) { set_error("chain: spike %d index %d out of bounds for axis of length %d", s, idx, n); return MVTB_EINVAL; }
+            d->sp[s].idx[a] = idx;
+            if (a < d->mask_ndim) {
+                const long long dd = d->mask_kind == MVTB_MASK_DISK ? (long long)(idx - n / 2) : (long long)(2 * idx - (n - 1));
+                q += dd * dd;
+            }
+        }
+        d->sp[s].amp = u->spikes[s].amplitude;
+        d->sp[s].mask_at_spike = d->mask_kind == MVTB_MASK_NONE ? 1 : (((q <= d->thr) ? 1 : 0) ^ d->inside_off);
+        for (int s2 = 0; s2 < s; ++s2) {
+            bool same = true;
+            for (int a = 0; a < p->ndim; ++a) same = same && d->sp[s2].idx[a] == d->sp[s].idx[a];
+            if (same) { set_error("chain: spikes %d and %d share a location (deduplicate on the host: the last one wins, F:937-938)", s2, s); return MVTB_EINVAL; }
+        }
+    }
+    return MVTB_OK;
+}
+
+static int launch_rows_fwd(const mvtb_plan* p, const float* in, cf* ws, long long n_rows, void* stream) {
+    const long long n_pairs = (n_rows + 1) / 2;
+    const int rp = p->rows_pairs_per_cta;
+    const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
+    const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
+    MVTB_LAUNCH(k_rows_fwd, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows);
+    return MVTB_OK;
+}
+
+template <int MODE>
+static int launch_axis(const mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const ChainGeom& g,
+                       const DescPack& pack, double* sums, void* stream) {
+    long long inner = p->nh;
+    for (int b = 1; b < axis; ++b) inner *= p->shape[b];
+    long long outer = n_outer_vols;
+    for (int b = axis + 1; b < p->ndim; ++b) outer *= p->shape[b];
+    const int T = p->axis_tile;
+    const long long ntiles = (inner + T - 1) / T;
+    const long long blocks = ntiles * outer;
+    if (blocks > 0x7fffffffLL) { set_error("chain: grid too large"); return MVTB_EUNSUPPORTED; }
+    const size_t smem = (size_t)p->shape[axis] * T * sizeof(cf);
+    auto kern = k_axis<MODE>;
+    MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums);
+    return MVTB_OK;
+}
+
+}  // namespace mvtb
+
+using namespace mvtb;
+
+extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, int n_volumes,
+                                     const mvtb_chain_desc* desc, int n_desc,
+                                     float* minmax_out, int vols_per_sample, void* stream) {
+    if (!p || !in || !out || !desc) { set_error("chain: null argument"); return MVTB_EINVAL; }
+    if (n_volumes < 0) { set_error("chain: n_volumes=%d", n_volumes); return MVTB_EINVAL; }
+    if (n_desc != 1 && n_desc != n_volumes) { set_error("chain: n_desc=%d must be 1 or n_volumes=%d", n_desc, n_volumes); return MVTB_EINVAL; }
+    if (minmax_out && vols_per_sample < 1) { set_error("chain: vols_per_sample=%d", vols_per_sample); return MVTB_EINVAL; }
+    if (n_volumes == 0) return MVTB_OK;
+    MVTB_CUDA(cudaSetDevice(p->device));
+
+    const ChainGeom g = make_geom(p);
+    DescPack pack;
+    memset(&pack, 0, sizeof(pack));
+    DescPack none;
+    memset(&none, 0, sizeof(none));
+    none.n = 1;
+    if (n_desc == 1) {
+        pack.n = 1;
+        int rc = convert_desc(p, desc, &pack.d[0]);
+        if (rc != MVTB_OK) return rc;
+    } else {
+        DescDev tmp;
+        for (int v = 0; v < n_volumes; ++v) {          // validate everything before launching anything
+            int rc = convert_desc(p, desc + v, &tmp);
+            if (rc != MVTB_OK) return rc;
+        }
+    }
+    long long rows_per_vol = 1;
+    for (int a = 1; a < p->ndim; ++a) rows_per_vol *= p->shape[a];
+
+    if (minmax_out) {
+        const int n_samples = (n_volumes + vols_per_sample - 1) / vols_per_sample;
+        MVTB_LAUNCH(k_minmax_init, dim3((n_samples + 127) / 128), dim3(128), 0, stream, minmax_out, n_samples);
+    }
+
+    const int mid = p->ndim - 1;
+    for (int v0 = 0; v0 < n_volumes; v0 += p->chunk) {
+        const int nv = (n_volumes - v0 < p->chunk) ? (n_volumes - v0) : p->chunk;
+        const long long n_rows = rows_per_vol * nv;
+        int rc = launch_rows_fwd(p, in + (size_t)v0 * p->vol_real, p->ws, n_rows, stream);
+        if (rc != MVTB_OK) return rc;
+        for (int a = 1; a < mid; ++a) {
+            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, none, nullptr, stream);
+            if (rc != MVTB_OK) return rc;
+        }
+        if (n_desc == 1) {
+            rc = launch_axis<AX_MID>(p, p->ws, mid, nv, g, pack, nullptr, stream);
+            if (rc != MVTB_OK) return rc;
+        } else {
+            for (int w0 = 0; w0 < nv; w0 += MVTB_DESC_PACK) {
+                const int nw = (nv - w0 < MVTB_DESC_PACK) ? (nv - w0) : MVTB_DESC_PACK;
+                pack.n = nw == 1 ? 1 : nw;
+                for (int i = 0; i < nw; ++i) convert_desc(p, desc + v0 + w0 + i, &pack.d[i]);
+                rc = launch_axis<AX_MID>(p, p->ws + (size_t)w0 * p->vol_half, mid, nw, g, pack, nullptr, stream);
+                if (rc != MVTB_OK) return rc;
+            }
+        }
+        for (int a = mid - 1; a >= 1; --a) {
+            rc = launch_axis<AX_INV>(p, p->ws, a, nv, g, none, nullptr, stream);
+            if (rc != MVTB_OK) return rc;
+        }
+        {
+            const long long n_pairs = (n_rows + 1) / 2;
+            const int rp = p->rows_pairs_per_cta;
+            const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
+            const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
+            const long long rows_per_sample = rows_per_vol * (minmax_out ? vols_per_sample : 1);
+            // chunks need not align with samples: the kernel works from the global row number
+            MVTB_LAUNCH(k_rows_inv, dim3(grid), dim3(kThreads), smem, stream, (const cf*)p->ws,
+                        out + (size_t)v0 * p->vol_real, p->ax[0], p->nh, p->row_pitch, rp, n_rows,
+                        minmax_out, rows_per_sample, rows_per_vol * (long long)v0);
+        }
+    }
+    MVTB_CUDA(cudaGetLastError());
+    return MVTB_OK;
+}
+
+extern "C" int mvtb_kspace_logabs_sum_f32(mvtb_plan* p, const float* in, int n_volumes, double* sums_out, void* stream) {
+    if (!p || !in || !sums_out) { set_error("logabs_sum: null argument"); return MVTB_EINVAL; }
+    if (n_volumes < 0) { set_error("logabs_sum: n_volumes=%d", n_volumes); return MVTB_EINVAL; }
+    if (n_volumes == 0) return MVTB_OK;
+    MVTB_CUDA(cudaSetDevice(p->device));
+    MVTB_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(double) * (size_t)n_volumes, (cudaStream_t)stream));
+    const ChainGeom g = make_geom(p);
+    DescPack none;
+    memset(&none, 0, sizeof(none));
+    none.n = 1;
+    long long rows_per_vol = 1;
+    for (int a = 1; a < p->ndim; ++a) rows_per_vol *= p->shape[a];
+    const int mid = p->ndim - 1;
+    for (int v0 = 0; v0 < n_volumes; v0 += p->chunk) {
+        const int nv = (n_volumes - v0 < p->chunk) ? (n_volumes - v0) : p->chunk;
+        int rc = launch_rows_fwd(p, in + (size_t)v0 * p->vol_real, p->ws, rows_per_vol * nv, stream);
+        if (rc != MVTB_OK) return rc;
+        for (int a = 1; a < mid; ++a) {
+            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, none, nullptr, stream);
+            if (rc != MVTB_OK) return rc;
+        }
+        rc = launch_axis<AX_STATS>(p, p->ws, mid, nv, g, none, sums_out + v0, stream);
+        if (rc != MVTB_OK) return rc;
+    }
+    MVTB_CUDA(cudaGetLastError());
+    return MVTB_OK;
+}

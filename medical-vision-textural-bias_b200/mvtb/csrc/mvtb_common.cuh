@@ -1,0 +1,100 @@
+// mvtb_common.cuh — shared declarations for the libmvtb kernels (sm_100a).
+//
+// The sources also compile with g++ -DMVTB_EMU against tests/cuemu/cuemu.h (a debug-only
+// fiber emulator used in the GPU-less build container to exercise index arithmetic); every
+// difference between the two builds is confined to the MVTB_EMU blocks in this header.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef MVTB_EMU
+#include "cuemu.h"
+#define MVTB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    cuemu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
+#define MVTB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
+#define MVTB_UNROLL
+#else
+#include <cuda_runtime.h>
+#define MVTB_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define MVTB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#define MVTB_UNROLL _Pragma("unroll")
+#endif
+
+#include "../../../include/mvtb.h"
+
+namespace mvtb {
+
+// ---------------------------------------------------------------- error plumbing
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);   // records text, returns (int)e
+
+#define MVTB_CUDA(call)                                         \
+    do {                                                        \
+        cudaError_t e_ = (call);                                \
+        if (e_ != cudaSuccess) return mvtb::cuda_fail(e_, #call); \
+    } while (0)
+
+// ---------------------------------------------------------------- complex helpers
+typedef float2 cf;
+__device__ __forceinline__ cf cmk(float x, float y) { cf r; r.x = x; r.y = y; return r; }
+__device__ __forceinline__ cf cadd(cf a, cf b) { return cmk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cf csub(cf a, cf b) { return cmk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cf cmul(cf a, cf b) { return cmk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cf cmulc(cf a, cf b) { return cmk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+__device__ __forceinline__ cf cconj(cf a) { return cmk(a.x, -a.y); }
+__device__ __forceinline__ cf cscale(cf a, float s) { return cmk(a.x * s, a.y * s); }
+__device__ __forceinline__ cf cmuli(cf a) { return cmk(-a.y, a.x); }    // a * (+i)
+__device__ __forceinline__ cf cmulni(cf a) { return cmk(a.y, -a.x); }   // a * (-i)
+
+// ---------------------------------------------------------------- per-axis FFT description
+#define MVTB_MAX_STAGES 12
+struct AxisDev {
+    int n;                       // axis length
+    int nstage;                  // radix stages
+    int radix[MVTB_MAX_STAGES];  // forward (DIF) order
+    const cf* tw;                // tw[t] = exp(-2 pi i t / n), t in [0, n)
+    const int* pos2k;            // position after the in-place DIF  ->  frequency bin
+    const int* k2pos;            // inverse map
+};
+
+// device view of mvtb_chain_desc, prepared on the host
+struct SpikeDev {
+    int idx[MVTB_MAX_FFT_DIMS];  // shifted index per FFT axis, axis 0 = LAST (contiguous) axis
+    float amp;
+    int mask_at_spike;           // M(f_s) in {0,1}
+};
+struct DescDev {
+    int mask_kind, mask_ndim;
+    long long thr;
+    int inside_off, n_spikes;
+    float wrap_alpha;
+    int wrap_naxes;
+    SpikeDev sp[MVTB_MAX_SPIKES];
+};
+#define MVTB_DESC_PACK 8
+struct DescPack {
+    int n;                       // 1 (shared) or number of volumes in this launch
+    DescDev d[MVTB_DESC_PACK];
+};
+
+}  // namespace mvtb
+
+struct mvtb_plan {
+    int ndim;                             // FFT rank (2..4)
+    int shape[MVTB_MAX_FFT_DIMS];         // axis 0 = LAST (contiguous) axis ... axis ndim-1 = outermost
+    int nh;                               // shape[0]/2 + 1
+    int chunk;                            // volumes in flight
+    int device;
+    int num_sms;
+    size_t vol_real;                      // floats per volume
+    size_t vol_half;                      // complex per volume half-spectrum
+    mvtb::AxisDev ax[MVTB_MAX_FFT_DIMS];  // device tables
+    void* table_mem;                      // one allocation behind all tables
+    mvtb::cf* ws;                         // chunk * vol_half complex
+    size_t ws_bytes;
+    // rows kernels geometry
+    int row_pitch;                        // complex slots per row pair in shared memory (odd)
+    int rows_pairs_per_cta;
+    int axis_tile;                        // columns per CTA in the axis kernels
+};

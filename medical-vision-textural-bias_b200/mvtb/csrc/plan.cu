@@ -1,0 +1,205 @@
+// plan.cu — FFT plan: factorisation, twiddle / digit-reversal tables, workspace; error text.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "mvtb_common.cuh"
+
+namespace mvtb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+int configure_chain_kernels(const mvtb_plan* p);   // kspace_chain.cu: opt in to large dynamic shared memory
+
+// prime factors <= 31, twos paired into fours, ascending (the radix-31 stage comes last,
+// where the DIF stage has no twiddle multiplies)
+static bool factorise(int n, std::vector<int>& out) {
+    static const int primes[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31};
+    int twos = 0;
+    std::vector<int> odd;
+    for (int p : primes) {
+        while (n % p == 0) {
+            if (p == 2) ++twos; else odd.push_back(p);
+            n /= p;
+        }
+    }
+    if (n != 1) return false;
+    out.clear();
+    if (twos & 1) out.push_back(2);
+    for (int i = 0; i < twos / 2; ++i) out.push_back(4);
+    // keep ascending order overall
+    std::vector<int> all(out);
+    all.insert(all.end(), odd.begin(), odd.end());
+    for (size_t i = 1; i < all.size(); ++i)
+        for (size_t j = i; j > 0 && all[j - 1] > all[j]; --j) { int t = all[j]; all[j] = all[j - 1]; all[j - 1] = t; }
+    out = all;
+    return (int)out.size() <= MVTB_MAX_STAGES;
+}
+
+}  // namespace mvtb
+
+using namespace mvtb;
+
+extern "C" int mvtb_version(void) { return MVTB_VERSION; }
+
+extern "C" int mvtb_last_error(char* buf, int n) {
+    int len = (int)strlen(g_err);
+    if (buf && n > 0) {
+        int c = len < n - 1 ? len : n - 1;
+        memcpy(buf, g_err, c);
+        buf[c] = 0;
+    }
+    return len;
+}
+
+extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_shape, int chunk_volumes, int device) {
+    if (!out || !fft_shape) { set_error("plan_create: null argument"); return MVTB_EINVAL; }
+    *out = nullptr;
+    if (ndim_fft < 2 || ndim_fft > MVTB_MAX_FFT_DIMS) { set_error("plan_create: ndim_fft=%d not in 2..4", ndim_fft); return MVTB_EINVAL; }
+    if (chunk_volumes < 1) { set_error("plan_create: chunk_volumes must be >= 1"); return MVTB_EINVAL; }
+    for (int i = 0; i < ndim_fft; ++i)
+        if (fft_shape[i] < 1) { set_error("plan_create: axis %d has length %d", i, fft_shape[i]); return MVTB_EINVAL; }
+
+#ifndef MVTB_EMU
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        set_error("plan_create: CUDA device %d not available (%d visible); libmvtb has no CPU path", device, ndev);
+        return MVTB_ENODEVICE;
+    }
+#endif
+    MVTB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MVTB_CUDA(cudaGetDeviceProperties(&prop, device));
+
+    mvtb_plan* p = (mvtb_plan*)calloc(1, sizeof(mvtb_plan));
+    if (!p) return MVTB_ENOMEM;
+    p->ndim = ndim_fft;
+    p->chunk = chunk_volumes;
+    p->device = device;
+    p->num_sms = prop.multiProcessorCount;
+    for (int a = 0; a < ndim_fft; ++a) p->shape[a] = fft_shape[ndim_fft - 1 - a];   // axis 0 = last
+    p->nh = p->shape[0] / 2 + 1;
+    p->vol_real = 1;
+    p->vol_half = (size_t)p->nh;
+    for (int a = 0; a < ndim_fft; ++a) p->vol_real *= (size_t)p->shape[a];
+    for (int a = 1; a < ndim_fft; ++a) p->vol_half *= (size_t)p->shape[a];
+
+    // ---- tables (one host image, one device allocation)
+    std::vector<std::vector<int>> radices(ndim_fft);
+    size_t bytes = 0;
+    for (int a = 0; a < ndim_fft; ++a) {
+        if (!factorise(p->shape[a], radices[a])) {
+            set_error("plan_create: axis length %d has a prime factor > 31 (unsupported)", p->shape[a]);
+            free(p);
+            return MVTB_EUNSUPPORTED;
+        }
+        bytes += (size_t)p->shape[a] * (sizeof(cf) + 2 * sizeof(int));
+        bytes = (bytes + 15) & ~(size_t)15;
+    }
+    std::vector<unsigned char> host(bytes);
+    void* dev = nullptr;
+    cudaError_t e = cudaMalloc(&dev, bytes);
+    if (e != cudaSuccess) { free(p); return cuda_fail(e, "cudaMalloc(tables)"); }
+    size_t off = 0;
+    for (int a = 0; a < ndim_fft; ++a) {
+        const int n = p->shape[a];
+        AxisDev& ax = p->ax[a];
+        ax.n = n;
+        ax.nstage = (int)radices[a].size();
+        for (int s = 0; s < ax.nstage; ++s) ax.radix[s] = radices[a][s];
+        cf* tw = (cf*)(host.data() + off);
+        ax.tw = (const cf*)((unsigned char*)dev + off);
+        for (int t = 0; t < n; ++t) {
+            double ang = -2.0 * M_PI * (double)t / (double)n;
+            tw[t].x = (float)cos(ang);
+            tw[t].y = (float)sin(ang);
+        }
+        off += (size_t)n * sizeof(cf);
+        int* pos2k = (int*)(host.data() + off);
+        ax.pos2k = (const int*)((unsigned char*)dev + off);
+        off += (size_t)n * sizeof(int);
+        int* k2pos = (int*)(host.data() + off);
+        ax.k2pos = (const int*)((unsigned char*)dev + off);
+        off += (size_t)n * sizeof(int);
+        off = (off + 15) & ~(size_t)15;
+        for (int pos = 0; pos < n; ++pos) {
+            int rem = pos, L = n, k = 0, mult = 1;
+            for (int s = 0; s < ax.nstage; ++s) {
+                const int R = ax.radix[s], m = L / R, q = rem / m;
+                rem -= q * m;
+                k += q * mult;
+                mult *= R;
+                L = m;
+            }
+            pos2k[pos] = k;
+            k2pos[k] = pos;
+        }
+    }
+    e = cudaMemcpy(dev, host.data(), bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(dev); free(p); return cuda_fail(e, "cudaMemcpy(tables)"); }
+    p->table_mem = dev;
+
+    // ---- kernel geometry
+    int pitch = 2 * p->nh;
+    if ((pitch & 1) == 0) ++pitch;
+    p->row_pitch = pitch;
+    const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
+    size_t per_pair = (size_t)pitch * sizeof(cf);
+    int rp = (int)((size_t)64 * 1024 / per_pair);
+    if (rp > 64) rp = 64;
+    if (rp < 1) rp = 1;
+    if (per_pair > smem_cap) {
+        set_error("plan_create: last axis of length %d does not fit in shared memory", p->shape[0]);
+        cudaFree(dev); free(p);
+        return MVTB_EUNSUPPORTED;
+    }
+    p->rows_pairs_per_cta = rp;
+    p->axis_tile = 16;
+    for (int a = 1; a < ndim_fft; ++a) {
+        while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) p->axis_tile /= 2;
+        if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) {
+            set_error("plan_create: axis of length %d does not fit in shared memory", p->shape[a]);
+            cudaFree(dev); free(p);
+            return MVTB_EUNSUPPORTED;
+        }
+    }
+
+    // ---- workspace
+    p->ws_bytes = (size_t)chunk_volumes * p->vol_half * sizeof(cf);
+    e = cudaMalloc((void**)&p->ws, p->ws_bytes);
+    if (e != cudaSuccess) { cudaFree(dev); free(p); return cuda_fail(e, "cudaMalloc(workspace)"); }
+
+    int rc = configure_chain_kernels(p);
+    if (rc != MVTB_OK) { cudaFree(p->ws); cudaFree(dev); free(p); return rc; }
+    *out = p;
+    return MVTB_OK;
+}
+
+extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
+    if (!p) return MVTB_OK;
+    cudaSetDevice(p->device);
+    cudaDeviceSynchronize();
+    if (p->ws) cudaFree(p->ws);
+    if (p->table_mem) cudaFree(p->table_mem);
+    free(p);
+    return MVTB_OK;
+}
+
+extern "C" size_t mvtb_plan_workspace_bytes(const mvtb_plan* p) { return p ? p->ws_bytes : 0; }

@@ -1,0 +1,53 @@
+"""numpy Philox4x32-10 — TEST INFRASTRUCTURE ONLY.
+
+Restates the published algorithm (Salmon, Moraes, Dror, Shaw: "Parallel random numbers: as easy
+as 1, 2, 3", SC'11; Random123 philox.h) and is pinned by Random123's own known-answer vectors
+(kat_vectors, philox4x32 10 rounds), checked in tests/test_host_logic.py.  The CUDA kernel's
+generator (csrc/voxel_ops.cu) is compared against this bit for bit.
+"""
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+MASK = np.uint64(0xFFFFFFFF)
+
+# Random123 kat_vectors: (counter[4], key[2]) -> output[4]
+KAT = [
+    ((0x00000000, 0x00000000, 0x00000000, 0x00000000), (0x00000000, 0x00000000),
+     (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+    ((0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff),
+     (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+    ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+     (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+]
+
+
+def philox4x32_10(ctr, key):
+    """ctr: (n,4) uint32, key: (n,2) uint32 -> (n,4) uint32."""
+    c = [ctr[:, i].astype(np.uint64) for i in range(4)]
+    k0 = key[:, 0].astype(np.uint32).copy()
+    k1 = key[:, 1].astype(np.uint32).copy()
+    for _ in range(10):
+        p0 = M0 * c[0]
+        p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0.astype(np.uint64), lo1, hi0 ^ c[3] ^ k1.astype(np.uint64), lo0]
+        with np.errstate(over="ignore"):
+            k0 = (k0 + W0).astype(np.uint32)
+            k1 = (k1 + W1).astype(np.uint32)
+    return np.stack([v.astype(np.uint32) for v in c], axis=1)
+
+
+def uniform_f32(n, seed, offset):
+    """The uniforms mvtb_salt_pepper_f32 / mvtb_philox_uniform_f32 produce for elements 0..n-1."""
+    ng = (n + 3) // 4
+    g = np.arange(ng, dtype=np.uint64) + np.uint64(offset)
+    ctr = np.zeros((ng, 4), dtype=np.uint32)
+    ctr[:, 0] = (g & MASK).astype(np.uint32)
+    ctr[:, 1] = (g >> np.uint64(32)).astype(np.uint32)
+    key = np.empty((ng, 2), dtype=np.uint32)
+    key[:, 0] = np.uint32(seed & 0xFFFFFFFF)
+    key[:, 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
+    r = philox4x32_10(ctr, key).reshape(-1)[:n]
+    return ((r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
