@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the MRI artifact chain on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg1]
+
+A "step" is one pass of the hot path over one batch of synthetic volumes:
+  cfg2 (default, the configuration BASELINE.json's metric is quoted on): the 127-series chain
+       Gibbs disk r=12.5 -> plane-wave spike I=15 on the (55,55,30) shell -> wraparound 0.5 ->
+       salt-and-pepper 0.05 on 64 x (1x240x240x155) fp32 volumes per GPU;
+  cfg3: Gibbs disk r=12.5 -> salt-and-pepper 0.15 on (4x240x240x155) samples;
+  cfg1: Gibbs disk r=12.5 on 1x240x240x155 volumes (the reference's own CPU-runnable case).
+Prints ONE JSON line (rank 0).  `value` = volumes/s with inputs resident in HBM; `e2e` = the same
+metric through the public API with HOST buffers (pinned H2D of the inputs and D2H of the outputs
+inside the timed region); `roofline` = dominant kernel against the measured HBM peak;
+`cpu_baseline` = the oracle port of the reference timed on this box's host cores.
+With --impl reference only the CPU reference arm runs (rank 0), on the same config and metric.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "medical-vision-textural-bias_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SHAPE = (240, 240, 155)
+BYTES_PER_VOXEL = 8            # algorithmic: read fp32 once + write fp32 once
+FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+WORKLOADS = {
+    "cfg2": dict(name="chain-127: Gibbs disk r=12.5 + k-space spike I=15 on (55,55,30) shell + wraparound 0.5 + salt-and-pepper 0.05",
+                 channels=1, batch=64, r=12.5, spike=True, alpha=0.5, p=0.05),
+    "cfg3": dict(name="Gibbs disk r=12.5 + salt-and-pepper 0.15 on 4-channel samples",
+                 channels=4, batch=16, r=12.5, spike=False, alpha=None, p=0.15),
+    "cfg1": dict(name="Gibbs disk r=12.5 (RandFourierDiskMaskd)", channels=1, batch=64, r=12.5, spike=False, alpha=None, p=None),
+}
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def shard_range(total, rank, world):
+    """Contiguous slice of `total` units owned by `rank`."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def aggregate(stats, world):
+    """(max over ranks, sum over ranks) of a per-rank statistics vector: the only collective on the path.
+    NCCL on the GPUs (a few dozen bytes over NVLink), gloo in the CPU tests."""
+    if world <= 1:
+        return stats.clone(), stats.clone()
+    import torch.distributed as dist
+    mx, sm = stats.clone(), stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+    return mx, sm
+
+
+def spike_indices(first_sample, n):
+    """Per-sample spike location: RandomState(sample_index).randint over the cached (55,55,30) shell."""
+    from mvtb import host
+    shell = host.ellipsoid_shell(SHAPE, 55., 55., 30.)
+    return [tuple(int(v) for v in shell[np.random.RandomState(first_sample + i).randint(0, len(shell))]) for i in range(n)]
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step(cfg, sample_index, n_volumes):
+    """The reference's CPU path (oracle port, same torch op sequence) on n_volumes samples."""
+    from oracle import ref_port as P
+    C = cfg["channels"]
+    idxs = spike_indices(sample_index, n_volumes) if cfg["spike"] else [None] * n_volumes
+    for i in range(n_volumes):
+        x = P.synthetic_volume(sample_index + i, (C,) + SHAPE)
+        t0 = time.perf_counter()
+        y = P.fourier_disk_mask(x, cfg["r"], False)
+        if cfg["spike"]:
+            y = P.plane_wave_spike(y, idxs[i], 15.0)
+        if cfg["alpha"] is not None:
+            y = P.wrap_artifact(y, cfg["alpha"])
+        if cfg["p"] is not None:
+            y = P.salt_and_pepper(y, cfg["p"], torch.rand(y.size()))      # the reference draws u itself (F:472)
+        yield time.perf_counter() - t0
+
+
+def time_cpu_reference(cfg, n_volumes, warm=1):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    list(cpu_reference_step(cfg, 10_000, warm))
+    ts = list(cpu_reference_step(cfg, 0, n_volumes))
+    return n_volumes / sum(ts), cores, ts
+
+
+def run_reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    n_per_step = 1 if cfg["channels"] > 1 else 2
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    list(cpu_reference_step(cfg, 10_000, 1))
+    for _ in range(args.warmup):
+        list(cpu_reference_step(cfg, 20_000, n_per_step))
+    dt = 0.0                               # transform time only; generating the synthetic input is not timed
+    for s in range(args.steps):
+        dt += sum(cpu_reference_step(cfg, s * n_per_step, n_per_step))
+    value = args.steps * n_per_step / dt
+    sample = f"{n_per_step} sample(s) of {cfg['channels']}x240x240x155 per step, {args.steps} steps, torch {torch.__version__} CPU, {cores} threads"
+    line = {
+        "impl": "reference", "metric": "volumes/sec (240x240x155 fp32)", "value": value, "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % cfg["channels"],
+                   "volumes_per_step": n_per_step, "note": "reference CPU path = oracle/ref_port.py, the bit-identical restatement "
+                   "of filters_and_operators.py (the pure-Python reference cannot travel to the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def make_inputs(cfg, first_sample, dev):
+    """Synthetic BraTS-shaped batch generated on the device from per-sample seeds."""
+    B, C = cfg["batch"], cfg["channels"]
+    grids = torch.meshgrid([torch.linspace(-1, 1, n, device=dev) for n in SHAPE], indexing="ij")
+    support = (sum((g / 0.9) ** 2 for g in grids) < 1).to(torch.float32)
+    x = torch.empty((B, C) + SHAPE, dtype=torch.float32, device=dev)
+    for b in range(B):
+        g = torch.Generator(device=dev).manual_seed(1234 + first_sample + b)
+        x[b] = torch.randn((C,) + SHAPE, generator=g, dtype=torch.float32, device=dev) * support
+    return x
+
+
+def gpu_step(cfg, x, idxs, out, step):
+    from mvtb import functional as Fn, host, _lib
+    B, C = x.shape[0], x.shape[1]
+    thr = host.disk_threshold(cfg["r"], SHAPE)
+    amp = host.exp_f32(15.0)
+    descs = []
+    for b in range(B):
+        sp = [(idxs[b], amp)] if cfg["spike"] else []
+        d = host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=sp, wrap_alpha=cfg["alpha"])
+        descs.extend([d] * C)
+    if cfg["p"] is None:
+        return Fn.kspace_chain(x, 3, descs, out=out)
+    y, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C, out=out)
+    n4 = (x.numel() + 3) // 4
+    return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=step * n4, n_samples=B, mm=mm, out=y)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: the workload's)")
+    ap.add_argument("--cpu-volumes", type=int, default=6, help="bounded CPU-baseline sample (volumes)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(WORKLOADS[args.workload])
+    if args.batch:
+        cfg["batch"] = args.batch
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank)
+        return
+
+    import torch.distributed as dist
+    from mvtb import _lib, functional as Fn
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the mvtb hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    B, C = cfg["batch"], cfg["channels"]
+    first = rank * B                                   # weak scaling: every rank owns its own B samples; seeds from the global index
+    x = make_inputs(cfg, first, dev)
+    out = torch.empty_like(x)
+    idxs = spike_indices(first, B) if cfg["spike"] else None
+    vols_per_step = B * C
+    voxels = vols_per_step * SHAPE[0] * SHAPE[1] * SHAPE[2]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing
+    for s in range(max(args.warmup, 3)):
+        gpu_step(cfg, x, idxs, out, s)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = L.mvtb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        gpu_step(cfg, x, idxs, out, 100 + s)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = int(L.mvtb_launch_count() - launches0)
+    clocks = sampler.stop()
+    checksum = float(out.double().sum())
+
+    # ---- per-kernel device time (cudaEvents around every launch, on the launching stream)
+    plan = Fn.get_plan(SHAPE, vols_per_step, dev)
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    prof_steps = min(args.steps, 3)
+    sp_ms = []
+    for s in range(prof_steps):
+        gpu_step(cfg, x, idxs, out, 200 + s)
+    torch.cuda.synchronize(dev)
+    import ctypes as Ct
+    ms_sum = (Ct.c_double * _lib.K_KINDS)()
+    cnts = (Ct.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms_sum, cnts))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    kernels = {}
+    for k in range(_lib.K_KINDS):
+        if cnts[k]:
+            kernels[L.mvtb_kernel_name(k).decode()] = {"launches_per_step": cnts[k] / prof_steps, "ms_per_step": ms_sum[k] / prof_steps,
+                                                       "avg_launch_ms": ms_sum[k] / cnts[k]}
+    if cfg["p"] is not None:                          # the select pass is launched from Python: time it the same way
+        from mvtb import functional as Fn2
+        mm = Fn2.minmax(out, B)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for s in range(3):
+            Fn2.salt_pepper(out, cfg["p"], seed=1, offset=0, n_samples=B, mm=mm, out=out)
+        b.record()
+        torch.cuda.synchronize(dev)
+        kernels["k_salt_pepper<philox>"] = {"launches_per_step": 1, "ms_per_step": a.elapsed_time(b) / 3, "avg_launch_ms": a.elapsed_time(b) / 3}
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
+    peak, peak_src = peak_hbm()
+    roofline = None
+    if dom:
+        kd = kernels[dom]
+        units_per_launch = vols_per_step / kd["launches_per_step"]
+        alg_bytes = BYTES_PER_VOXEL * SHAPE[0] * SHAPE[1] * SHAPE[2] * units_per_launch
+        achieved = alg_bytes / (kd["avg_launch_ms"] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "share_of_step": kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values())}
+
+    # ---- end to end through the public API with host buffers (pinned H2D in, D2H out, every step)
+    e2e_steps = max(1, min(args.steps, 3))
+    hx = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+    hx.copy_(x)
+    hy = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+
+    def e2e_step(s):
+        xd = hx.to(dev, non_blocking=True)
+        y = gpu_step(cfg, xd, idxs, xd, 300 + s)          # in place on the staged copy
+        hy.copy_(y, non_blocking=True)
+
+    e2e_step(0)
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for s in range(e2e_steps):
+        e2e_step(s + 1)
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+
+    # ---- max over ranks, whole-job aggregate; NCCL only gathers statistics
+    stats = torch.tensor([ms, e2e_ms, float(B), checksum], dtype=torch.float64, device=dev)
+    mx, sm = aggregate(stats, world)
+    ms, e2e_ms = float(mx[0]), float(mx[1])
+    total_vols_per_step, checksum = float(sm[2]), float(sm[3])
+
+    if rank == 0:
+        value = total_vols_per_step * args.steps / (ms * 1e-3)
+        e2e_value = total_vols_per_step * e2e_steps / (e2e_ms * 1e-3)
+        step_bytes = BYTES_PER_VOXEL * voxels
+        line = {
+            "metric": "volumes/sec (240x240x155 fp32)", "value": value, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % C, "samples_per_gpu": B,
+                       "volumes_per_step_per_gpu": vols_per_step, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": "inputs larger than L2 (%.2f GB in + out per step per GPU)" % (2 * voxels * 4 / 1e9),
+                       "rng": "in-kernel Philox4x32-10"},
+            "channel_volumes_per_s": value * C,
+            "roofline": roofline,
+            "hbm_frac_whole_step": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+            "kernels": kernels,
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(voxels * 4), "d2h_bytes_per_step": int(voxels * 4),
+                    "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "checksum": checksum,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            nv = max(1, args.cpu_volumes // (C * C))
+            v, cores, ts = time_cpu_reference(cfg, nv)
+            line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port",
+                                    "sample": f"{nv} sample(s) of {C}x240x240x155 through oracle/ref_port.py (same torch op sequence as the reference), "
+                                              f"{cores} threads, {sum(ts):.1f} s"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -114,6 +114,20 @@ int mvtb_philox_uniform_f32(float* out, size_t n, uint64_t seed, uint64_t offset
  * (SURVEY A.3).  Returns MVTB_EUNSUPPORTED for an odd axis (use the chain). in != out. */
 int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W, int D, float alpha, void* stream);
 
+/* ---- measurement hooks (bench.py): per-kernel device time from cudaEvents recorded on the
+ * launching stream around every launch a plan makes, and a process-wide launch counter. */
+#define MVTB_K_ROWS_FWD 0
+#define MVTB_K_AXIS_FWD 1
+#define MVTB_K_AXIS_MID 2
+#define MVTB_K_AXIS_INV 3
+#define MVTB_K_ROWS_INV 4
+#define MVTB_K_KINDS 16
+int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
+/* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */
+int mvtb_plan_profile_read(mvtb_plan* plan, double* ms_sum, int* counts);
+const char* mvtb_kernel_name(int kind);
+unsigned long long mvtb_launch_count(void);           /* kernels launched by this library so far */
+
 #ifdef __cplusplus
 }
 #endif

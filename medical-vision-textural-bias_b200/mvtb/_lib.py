@@ -52,7 +52,12 @@ _SYMBOLS = {
                                        C.c_float, C.c_void_p, C.c_void_p]),
     "mvtb_philox_uniform_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mvtb_wrap_fold_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "mvtb_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "mvtb_plan_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "mvtb_kernel_name": (C.c_char_p, [C.c_int]),
+    "mvtb_launch_count": (C.c_ulonglong, []),
 }
+K_KINDS = 16
 
 
 def bind(cdll):

@@ -380,7 +380,8 @@ static int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d
     return MVTB_OK;
 }
 
-static int launch_rows_fwd(const mvtb_plan* p, const float* in, cf* ws, long long n_rows, void* stream) {
+static int launch_rows_fwd(mvtb_plan* p, const float* in, cf* ws, long long n_rows, void* stream) {
+    ProfScope prof(p, MVTB_K_ROWS_FWD, stream);
     const long long n_pairs = (n_rows + 1) / 2;
     const int rp = p->rows_pairs_per_cta;
     const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
@@ -390,8 +391,9 @@ static int launch_rows_fwd(const mvtb_plan* p, const float* in, cf* ws, long lon
 }
 
 template <int MODE>
-static int launch_axis(const mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const ChainGeom& g,
+static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const ChainGeom& g,
                        const DescPack& pack, double* sums, void* stream) {
+    ProfScope prof(p, MODE == AX_FWD ? MVTB_K_AXIS_FWD : (MODE == AX_INV ? MVTB_K_AXIS_INV : MVTB_K_AXIS_MID), stream);
     long long inner = p->nh;
     for (int b = 1; b < axis; ++b) inner *= p->shape[b];
     long long outer = n_outer_vols;
@@ -478,6 +480,7 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
             const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
             const long long rows_per_sample = rows_per_vol * (minmax_out ? vols_per_sample : 1);
             // chunks need not align with samples: the kernel works from the global row number
+            ProfScope prof(p, MVTB_K_ROWS_INV, stream);
             MVTB_LAUNCH(k_rows_inv, dim3(grid), dim3(kThreads), smem, stream, (const cf*)p->ws,
                         out + (size_t)v0 * p->vol_real, p->ax[0], p->nh, p->row_pitch, rp, n_rows,
                         minmax_out, rows_per_sample, rows_per_vol * (long long)v0);

@@ -10,13 +10,13 @@
 #ifdef MVTB_EMU
 #include "cuemu.h"
 #define MVTB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    cuemu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); })
+    do { mvtb::count_launch(); cuemu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)
 #define MVTB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
 #define MVTB_UNROLL
 #else
 #include <cuda_runtime.h>
 #define MVTB_LAUNCH(kern, grid, block, smem, stream, ...) \
-    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+    do { mvtb::count_launch(); kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define MVTB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define MVTB_UNROLL _Pragma("unroll")
 #endif
@@ -27,6 +27,7 @@ namespace mvtb {
 
 // ---------------------------------------------------------------- error plumbing
 void set_error(const char* fmt, ...);
+void count_launch();
 int cuda_fail(cudaError_t e, const char* what);   // records text, returns (int)e
 
 #define MVTB_CUDA(call)                                         \
@@ -80,6 +81,7 @@ struct DescPack {
 
 }  // namespace mvtb
 
+#define MVTB_PROF_MAX 2048
 struct mvtb_plan {
     int ndim;                             // FFT rank (2..4)
     int shape[MVTB_MAX_FFT_DIMS];         // axis 0 = LAST (contiguous) axis ... axis ndim-1 = outermost
@@ -97,4 +99,30 @@ struct mvtb_plan {
     int row_pitch;                        // complex slots per row pair in shared memory (odd)
     int rows_pairs_per_cta;
     int axis_tile;                        // columns per CTA in the axis kernels
+    // measurement hooks (mvtb_plan_profile*)
+    int profiling;
+    int prof_n;
+    int prof_kind[MVTB_PROF_MAX];
+    cudaEvent_t prof_ev[2 * MVTB_PROF_MAX];
+    double prof_ms[MVTB_K_KINDS];
+    int prof_cnt[MVTB_K_KINDS];
 };
+
+namespace mvtb {
+// brackets one launch with events when the plan is recording
+struct ProfScope {
+    mvtb_plan* p;
+    void* stream;
+    int slot;
+    ProfScope(mvtb_plan* plan, int kind, void* st) : p(plan), stream(st), slot(-1) {
+        if (p && p->profiling && p->prof_n < MVTB_PROF_MAX) {
+            slot = p->prof_n++;
+            p->prof_kind[slot] = kind;
+            cudaEventRecord(p->prof_ev[2 * slot], (cudaStream_t)stream);
+        }
+    }
+    ~ProfScope() {
+        if (slot >= 0) cudaEventRecord(p->prof_ev[2 * slot + 1], (cudaStream_t)stream);
+    }
+};
+}  // namespace mvtb

@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "mvtb_common.cuh"
@@ -19,6 +20,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
     set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
@@ -198,7 +202,46 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     cudaDeviceSynchronize();
     if (p->ws) cudaFree(p->ws);
     if (p->table_mem) cudaFree(p->table_mem);
+    if (p->prof_ev[0])
+        for (int i = 0; i < 2 * MVTB_PROF_MAX; ++i) cudaEventDestroy(p->prof_ev[i]);
     free(p);
+    return MVTB_OK;
+}
+
+extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load(); }
+
+extern "C" const char* mvtb_kernel_name(int kind) {
+    static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
+                                              "k_bl_fwd", "k_bl_mid", "k_bl_inv", "", "", "", "", "", "", "", ""};
+    return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
+}
+
+extern "C" int mvtb_plan_profile(mvtb_plan* p, int enable) {
+    if (!p) { set_error("plan_profile: null plan"); return MVTB_EINVAL; }
+    MVTB_CUDA(cudaSetDevice(p->device));
+    if (enable) {
+        if (!p->prof_ev[0])
+            for (int i = 0; i < 2 * MVTB_PROF_MAX; ++i) MVTB_CUDA(cudaEventCreate(&p->prof_ev[i]));
+        p->prof_n = 0;
+        memset(p->prof_ms, 0, sizeof(p->prof_ms));
+        memset(p->prof_cnt, 0, sizeof(p->prof_cnt));
+    }
+    p->profiling = enable ? 1 : 0;
+    return MVTB_OK;
+}
+
+extern "C" int mvtb_plan_profile_read(mvtb_plan* p, double* ms_sum, int* counts) {
+    if (!p || !ms_sum || !counts) { set_error("plan_profile_read: null argument"); return MVTB_EINVAL; }
+    MVTB_CUDA(cudaSetDevice(p->device));
+    for (int i = 0; i < p->prof_n; ++i) {
+        MVTB_CUDA(cudaEventSynchronize(p->prof_ev[2 * i + 1]));
+        float ms = 0.f;
+        MVTB_CUDA(cudaEventElapsedTime(&ms, p->prof_ev[2 * i], p->prof_ev[2 * i + 1]));
+        p->prof_ms[p->prof_kind[i]] += ms;
+        p->prof_cnt[p->prof_kind[i]] += 1;
+    }
+    p->prof_n = 0;
+    for (int k = 0; k < MVTB_K_KINDS; ++k) { ms_sum[k] = p->prof_ms[k]; counts[k] = p->prof_cnt[k]; }
     return MVTB_OK;
 }
 

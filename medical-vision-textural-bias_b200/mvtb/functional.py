@@ -1,0 +1,193 @@
+"""Tensor-level entry points over the C ABI (include/mvtb.h): torch supplies device memory and
+streams, libmvtb.so does the arithmetic.  No function here has a CPU implementation; on a
+machine without CUDA they raise.
+
+Layout contract (same as the reference): contiguous float32, FFT over the last `ndim_fft` axes,
+every leading axis is a batch of independent volumes.
+"""
+import atexit
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, host
+
+# in-flight half-spectra per plan: ~2 volumes of 240x240x155 so the workspace can stay L2-resident
+_WS_TARGET_BYTES = 80 << 20
+_plans = {}
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("mvtb: no CUDA device is available and there is no CPU fallback "
+                           "(the transforms run only through libmvtb.so on a GPU)")
+
+
+def _stream(dev: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(x, device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.device]:
+    """float32 contiguous CUDA view/copy of x, plus the device x came from (results go back there)."""
+    require_cuda()
+    if isinstance(x, np.ndarray):
+        x = torch.as_tensor(x)
+    if not isinstance(x, torch.Tensor):
+        raise TypeError(f"expected a torch.Tensor or numpy array, got {type(x).__name__}")
+    if x.dtype != torch.float32:
+        raise TypeError(f"mvtb kernels are float32-only (got {x.dtype}); the reference pipelines are float32 as well")
+    src = x.device
+    if x.is_cuda:
+        return x.contiguous(), src
+    dev = device or torch.device("cuda", torch.cuda.current_device())
+    return x.contiguous().to(dev, non_blocking=False), src
+
+
+def back(y: torch.Tensor, src: torch.device) -> torch.Tensor:
+    return y if src == y.device else y.to(src)
+
+
+def get_plan(fft_shape: Sequence[int], n_volumes: int, dev: torch.device):
+    fft_shape = tuple(int(s) for s in fft_shape)
+    nh = fft_shape[-1] // 2 + 1
+    half_bytes = 8 * nh * int(np.prod(fft_shape[:-1]))
+    chunk = int(max(1, min(n_volumes, _WS_TARGET_BYTES // max(half_bytes, 1))))
+    if chunk > 8:
+        chunk = 1 << (chunk.bit_length() - 1)        # few distinct plans per shape
+    key = (dev.index, fft_shape, chunk)
+    h = _plans.get(key)
+    if h is None:
+        L = _lib.lib()
+        h = C.c_void_p()
+        shp = (C.c_int * len(fft_shape))(*fft_shape)
+        _lib.check(L, L.mvtb_plan_create(C.byref(h), len(fft_shape), shp, chunk, dev.index))
+        _plans[key] = h
+    return h
+
+
+@atexit.register
+def _destroy_plans():
+    if _plans and _lib._lib is not None:
+        for h in _plans.values():
+            try:
+                _lib._lib.mvtb_plan_destroy(h)
+            except Exception:  # noqa: BLE001
+                pass
+        _plans.clear()
+
+
+def kspace_chain(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc], *, want_minmax: bool = False,
+                 vols_per_sample: int = 1, out: Optional[torch.Tensor] = None):
+    """out = Re ifftn(W (M fftn(x) + spikes)) over the last ndim_fft axes of a CUDA float32 tensor.
+
+    descs: one shared descriptor or one per volume (volumes = product of the leading axes).
+    Returns y, or (y, minmax[n_samples, 2]) when want_minmax."""
+    L = _lib.lib()
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("kspace_chain expects a contiguous float32 CUDA tensor (use functional.to_device)")
+    if x.dim() < ndim_fft:
+        raise ValueError(f"input of rank {x.dim()} has fewer than ndim_fft={ndim_fft} axes")
+    fft_shape = tuple(x.shape[-ndim_fft:])
+    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    if len(descs) not in (1, nvol):
+        raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
+    y = torch.empty_like(x) if out is None else out
+    if x.numel() == 0:
+        return (y, torch.empty((0, 2), device=x.device)) if want_minmax else y
+    plan = get_plan(fft_shape, nvol, x.device)
+    mm = None
+    if want_minmax:
+        mm = torch.empty(((nvol + vols_per_sample - 1) // vols_per_sample, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_kspace_chain_f32(plan, _ptr(x), _ptr(y), nvol, host.desc_array(descs), len(descs), _ptr(mm),
+                                     int(vols_per_sample), _stream(x.device))
+    _lib.check(L, rc)
+    return (y, mm) if want_minmax else y
+
+
+def logabs_mean25(x: torch.Tensor, ndim_fft: int) -> torch.Tensor:
+    """2.5 * mean(log(|fftn(x)| + 1e-10)) per volume, float32 on x.device (F:932-933, F:1127-1129)."""
+    L = _lib.lib()
+    fft_shape = tuple(x.shape[-ndim_fft:])
+    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    plan = get_plan(fft_shape, nvol, x.device)
+    sums = torch.empty(nvol, dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_kspace_logabs_sum_f32(plan, _ptr(x), nvol, _ptr(sums), _stream(x.device))
+    _lib.check(L, rc)
+    return (sums * (2.5 / float(np.prod(fft_shape)))).to(torch.float32).reshape(x.shape[:-ndim_fft])
+
+
+def minmax(x: torch.Tensor, n_samples: int = 1) -> torch.Tensor:
+    """(min, max) per sample -> float32 [n_samples, 2] on x.device."""
+    L = _lib.lib()
+    mm = torch.empty((n_samples, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_minmax_f32(_ptr(x), x.numel() // max(n_samples, 1), n_samples, _ptr(mm), _stream(x.device))
+    _lib.check(L, rc)
+    return mm
+
+
+def salt_pepper(x: torch.Tensor, p: float, *, u: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
+                n_samples: int = 1, mm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Salt-and-pepper select (F:465-482) per sample; u injected (bit-exact parity) or Philox(seed, offset)."""
+    L = _lib.lib()
+    if mm is None:
+        mm = minmax(x, n_samples)
+    if u is not None and (u.shape != x.shape or u.dtype != torch.float32 or u.device != x.device or not u.is_contiguous()):
+        raise ValueError("u must be a contiguous float32 tensor of x's shape on x's device")
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_salt_pepper_f32(_ptr(x), _ptr(y), x.numel() // max(n_samples, 1), n_samples, _ptr(u),
+                                    C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset & (2 ** 64 - 1)),
+                                    C.c_float(p), _ptr(mm), _stream(x.device))
+    _lib.check(L, rc)
+    return y
+
+
+def philox_uniform(n: int, seed: int, offset: int, device: torch.device) -> torch.Tensor:
+    L = _lib.lib()
+    out = torch.empty(n, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = L.mvtb_philox_uniform_f32(_ptr(out), n, C.c_uint64(seed), C.c_uint64(offset), _stream(device))
+    _lib.check(L, rc)
+    return out
+
+
+def wrap_fold(x: torch.Tensor, alpha: float) -> torch.Tensor:
+    """Even-axis wraparound fold on (..., H, W, D); raises MvtbError(EUNSUPPORTED) for an odd axis."""
+    L = _lib.lib()
+    H, W, D = (int(s) for s in x.shape[-3:])
+    nvol = x.numel() // (H * W * D) if x.numel() else 0
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_wrap_fold_f32(_ptr(x), _ptr(y), nvol, H, W, D, C.c_float(alpha), _stream(x.device))
+    _lib.check(L, rc)
+    return y
+
+
+# ----------------------------------------------------------------------------- batched chain-127 convenience
+def chain127(x: torch.Tensor, *, r: float, spike_idx: Optional[Sequence[Sequence[int]]], intensity: float,
+             alpha: Optional[float], p: Optional[float], u: Optional[torch.Tensor] = None, seed: int = 0,
+             offset: int = 0) -> torch.Tensor:
+    """disk -> plane-wave spike -> wrap -> S&P on a batch (B, C, H, W, D), each (C,H,W,D) sample treated
+    exactly as one pass through the 127-series Compose (one spike location per sample, shared by its
+    channels; S&P min/max over the whole sample).  spike_idx: per-sample fftshift-ed (h,w,d), or None."""
+    B_, C_ = x.shape[0], x.shape[1]
+    thr = host.disk_threshold(r, x.shape[-3:])
+    amp = host.exp_f32(intensity)
+    descs: List[_lib.ChainDesc] = []
+    for b in range(B_):
+        sp = [(spike_idx[b], amp)] if spike_idx is not None else []
+        d = host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=sp, wrap_alpha=alpha)
+        descs.extend([d] * C_)
+    if p is None:
+        return kspace_chain(x, 3, descs)
+    y, mm = kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C_)
+    return salt_pepper(y, p, u=u, seed=seed, offset=offset, n_samples=B_, mm=mm, out=y)
