@@ -314,15 +314,28 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
 }
 
 // ------------------------------------------------------------------ host side
+#ifndef MVTB_EMU
+template <typename K>
+static int allow_big_smem(K kern, int optin) {
+    cudaFuncAttributes a;
+    MVTB_CUDA(cudaFuncGetAttributes(&a, kern));
+    MVTB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes));
+    return MVTB_OK;
+}
+#endif
+
 int configure_chain_kernels(const mvtb_plan* p) {
 #ifndef MVTB_EMU
-    const int big = 227 * 1024;
-    MVTB_CUDA(cudaFuncSetAttribute(k_rows_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    MVTB_CUDA(cudaFuncSetAttribute(k_rows_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_INV>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-    MVTB_CUDA(cudaFuncSetAttribute(k_axis<AX_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    cudaDeviceProp prop;
+    MVTB_CUDA(cudaGetDeviceProperties(&prop, p->device));
+    const int optin = (int)prop.sharedMemPerBlockOptin;
+    int rc;
+    if ((rc = allow_big_smem(k_rows_fwd, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_rows_inv, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_FWD>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_INV>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_MID>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_STATS>, optin)) != MVTB_OK) return rc;
 #endif
     (void)p;
     return MVTB_OK;

@@ -355,7 +355,7 @@ def test_properties_full_size(F, cuda_device):
     # identities: no mask = round trip; wrap alpha=1; S&P p=0 (F:437-438)
     assert rel_l2(Fn.kspace_chain(x, 3, [host.make_desc()]).cpu().numpy(), x.cpu().numpy()) <= TOL
     assert rel_l2(F.WrapArtifact(1.0)(x).cpu().numpy(), x.cpu().numpy()) <= TOL
-    assert torch.equal(F.SaltAndPepper(0.0).salt_and_pepper(x, u=torch.rand_like(x)), x)
+    assert torch.equal(F.SaltAndPepper(0.0).salt_and_pepper(x, u=torch.rand_like(x).clamp_min(1e-6)), x)   # u == 0 still hits `u <= p/2`, as in the reference
     # fold form == k-space form of the wraparound on an all-even shape
     xe = P.synthetic_volume(9, (2, 128, 128, 64)).to(cuda_device)
     a = Fn.wrap_fold(xe, 0.25)
