@@ -121,12 +121,24 @@ int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W,
 #define MVTB_K_AXIS_MID 2
 #define MVTB_K_AXIS_INV 3
 #define MVTB_K_ROWS_INV 4
+#define MVTB_K_BL_FWD_H 5
+#define MVTB_K_BL_FWD_W 6
+#define MVTB_K_BL_MID 7
+#define MVTB_K_BL_INV_W 8
+#define MVTB_K_BL_INV_H 9
 #define MVTB_K_KINDS 16
 int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
 /* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */
 int mvtb_plan_profile_read(mvtb_plan* plan, double* ms_sum, int* counts);
 const char* mvtb_kernel_name(int kind);
 unsigned long long mvtb_launch_count(void);           /* kernels launched by this library so far */
+
+/* Which kernels the chain uses: 0 = automatic (the band-limited pruned-DFT path when the mask is a
+ * small disk, else the general FFT path), 1 = always the general FFT path.  Both produce the same
+ * result to fp32 rounding; the switch exists for tests and measurements. */
+#define MVTB_PATH_AUTO 0
+#define MVTB_PATH_GENERAL 1
+int mvtb_plan_set_path(mvtb_plan* plan, int path);
 
 #ifdef __cplusplus
 }

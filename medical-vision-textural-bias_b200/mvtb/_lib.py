@@ -56,6 +56,7 @@ _SYMBOLS = {
     "mvtb_plan_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "mvtb_kernel_name": (C.c_char_p, [C.c_int]),
     "mvtb_launch_count": (C.c_ulonglong, []),
+    "mvtb_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
 }
 K_KINDS = 16
 

@@ -21,6 +21,11 @@
 
 namespace mvtb {
 
+// bandlimited.cu
+bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, int* F_out);
+int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
+             int F, float* minmax_out, int vols_per_sample, void* stream);
+
 enum { AX_FWD = 0, AX_INV = 1, AX_MID = 2, AX_STATS = 3 };
 static const int kThreads = 256;
 
@@ -357,7 +362,7 @@ static ChainGeom make_geom(const mvtb_plan* p) {
 }
 
 // validates one user descriptor against the plan and converts it to the device view
-static int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
+int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
     memset(d, 0, sizeof(*d));
     if (u->mask_kind < MVTB_MASK_NONE || u->mask_kind > MVTB_MASK_CENTRED) { set_error("chain: mask_kind=%d", u->mask_kind); return MVTB_EINVAL; }
     if (u->mask_kind != MVTB_MASK_NONE && (u->mask_ndim < 1 || u->mask_ndim > p->ndim)) { set_error("chain: mask_ndim=%d with ndim_fft=%d", u->mask_ndim, p->ndim); return MVTB_EINVAL; }
@@ -459,6 +464,10 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
         const int n_samples = (n_volumes + vols_per_sample - 1) / vols_per_sample;
         MVTB_LAUNCH(k_minmax_init, dim3((n_samples + 127) / 128), dim3(128), 0, stream, minmax_out, n_samples);
     }
+
+    int blF = 0;
+    if (bl_eligible(p, desc, n_desc, &blF))
+        return bl_chain(p, in, out, n_volumes, desc, n_desc, blF, minmax_out, vols_per_sample, stream);
 
     const int mid = p->ndim - 1;
     for (int v0 = 0; v0 < n_volumes; v0 += p->chunk) {

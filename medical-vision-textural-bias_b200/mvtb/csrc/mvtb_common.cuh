@@ -49,6 +49,7 @@ __device__ __forceinline__ cf cmuli(cf a) { return cmk(-a.y, a.x); }    // a * (
 __device__ __forceinline__ cf cmulni(cf a) { return cmk(a.y, -a.x); }   // a * (-i)
 
 // ---------------------------------------------------------------- per-axis FFT description
+struct DescDev;
 #define MVTB_MAX_STAGES 12
 struct AxisDev {
     int n;                       // axis length
@@ -82,6 +83,8 @@ struct DescPack {
 }  // namespace mvtb
 
 #define MVTB_PROF_MAX 2048
+#define MVTB_BL_FT 36                     // table columns: frequencies 0..35
+#define MVTB_BL_MAX_PW 2                  // out-of-box spikes per volume the inverse kernel adds as plane waves
 struct mvtb_plan {
     int ndim;                             // FFT rank (2..4)
     int shape[MVTB_MAX_FFT_DIMS];         // axis 0 = LAST (contiguous) axis ... axis ndim-1 = outermost
@@ -99,6 +102,10 @@ struct mvtb_plan {
     int row_pitch;                        // complex slots per row pair in shared memory (odd)
     int rows_pairs_per_cta;
     int axis_tile;                        // columns per CTA in the axis kernels
+    // band-limited path (bandlimited.cu): cos/sin tables per axis, [N][MVTB_BL_FT] each
+    int opt_path;
+    float* bl_tab;
+    size_t bl_off[3];
     // measurement hooks (mvtb_plan_profile*)
     int profiling;
     int prof_n;

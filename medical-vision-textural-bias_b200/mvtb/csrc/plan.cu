@@ -30,6 +30,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 int configure_chain_kernels(const mvtb_plan* p);   // kspace_chain.cu: opt in to large dynamic shared memory
+int configure_bl_kernels(const mvtb_plan* p);      // bandlimited.cu
 
 // prime factors <= 31, twos paired into fours, ascending (the radix-31 stage comes last,
 // where the DIF stage has no twiddle multiplies)
@@ -190,7 +191,30 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     e = cudaMalloc((void**)&p->ws, p->ws_bytes);
     if (e != cudaSuccess) { cudaFree(dev); free(p); return cuda_fail(e, "cudaMalloc(workspace)"); }
 
+    // ---- band-limited path tables: cos/sin(2 pi f n / N) for f < MVTB_BL_FT, per axis (3-D plans)
+    if (ndim_fft == 3) {
+        size_t nfl = 0;
+        for (int a = 0; a < 3; ++a) { p->bl_off[a] = nfl; nfl += (size_t)2 * p->shape[a] * MVTB_BL_FT; }
+        std::vector<float> tab(nfl);
+        for (int a = 0; a < 3; ++a) {
+            const int n = p->shape[a];
+            float* tc = tab.data() + p->bl_off[a];
+            float* ts = tc + (size_t)n * MVTB_BL_FT;
+            for (int i = 0; i < n; ++i)
+                for (int f = 0; f < MVTB_BL_FT; ++f) {
+                    const long long m = ((long long)f * i) % n;
+                    const double ang = 2.0 * M_PI * (double)m / (double)n;
+                    tc[(size_t)i * MVTB_BL_FT + f] = (float)cos(ang);
+                    ts[(size_t)i * MVTB_BL_FT + f] = (float)sin(ang);
+                }
+        }
+        e = cudaMalloc((void**)&p->bl_tab, nfl * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(p->bl_tab, tab.data(), nfl * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { cudaFree(p->ws); cudaFree(dev); free(p); return cuda_fail(e, "band-limited tables"); }
+    }
+
     int rc = configure_chain_kernels(p);
+    if (rc == MVTB_OK) rc = configure_bl_kernels(p);
     if (rc != MVTB_OK) { cudaFree(p->ws); cudaFree(dev); free(p); return rc; }
     *out = p;
     return MVTB_OK;
@@ -202,6 +226,7 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     cudaDeviceSynchronize();
     if (p->ws) cudaFree(p->ws);
     if (p->table_mem) cudaFree(p->table_mem);
+    if (p->bl_tab) cudaFree(p->bl_tab);
     if (p->prof_ev[0])
         for (int i = 0; i < 2 * MVTB_PROF_MAX; ++i) cudaEventDestroy(p->prof_ev[i]);
     free(p);
@@ -212,8 +237,14 @@ extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load()
 
 extern "C" const char* mvtb_kernel_name(int kind) {
     static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
-                                              "k_bl_fwd", "k_bl_mid", "k_bl_inv", "", "", "", "", "", "", "", ""};
+                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "", "", "", "", "", ""};
     return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
+}
+
+extern "C" int mvtb_plan_set_path(mvtb_plan* p, int path) {
+    if (!p || (path != MVTB_PATH_AUTO && path != MVTB_PATH_GENERAL)) { set_error("plan_set_path: bad argument"); return MVTB_EINVAL; }
+    p->opt_path = path;
+    return MVTB_OK;
 }
 
 extern "C" int mvtb_plan_profile(mvtb_plan* p, int enable) {

@@ -1,0 +1,104 @@
+"""Band-limited (pruned-DFT) path of the chain, run through the DEBUG emulator, against the
+general FFT path and the oracle.  Debug scaffolding for a GPU-less container, like
+tests/test_emu_kernels.py; the parity evidence for the CUDA build is tests/test_gpu_bandlimited.py."""
+import shutil
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, rel_l2
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++ for the emulator build")
+
+from cuemu import emu  # noqa: E402
+from mvtb import _lib as B, host  # noqa: E402
+from oracle import ref_port as P  # noqa: E402
+
+TOL = 1e-5
+
+
+def run(x, descs, general, chunk=4, vps=None):
+    L = emu.lib()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    plan = emu.Plan(x.shape[-3:], chunk)
+    B.check(L, L.mvtb_plan_set_path(plan.h, 1 if general else 0))
+    n0 = L.mvtb_launch_count()
+    y = np.empty_like(x)
+    nvol = int(np.prod(x.shape[:-3]))
+    mm = np.zeros(2 * ((nvol + vps - 1) // vps), dtype=np.float32) if vps else None
+    B.check(L, L.mvtb_kspace_chain_f32(plan.h, emu.ptr(x), emu.ptr(y), nvol, host.desc_array(descs), len(descs),
+                                       emu.ptr(mm), vps or 1, None))
+    return y, int(L.mvtb_launch_count() - n0), mm
+
+
+def disk(thr, **kw):
+    return host.make_desc(mask_kind=B.MASK_DISK, mask_ndim=3, mask_thresh=thr, **kw)
+
+
+@pytest.mark.parametrize("shape,r", [((2, 16, 12, 8), 2.5), ((1, 32, 32, 16), 4.0), ((1, 9, 15, 25), 2.5),
+                                     ((3, 12, 10, 31), 3.0), ((1, 30, 26, 27), 12.5)])
+def test_bl_matches_oracle_and_general(shape, r):
+    x = P.synthetic_volume(1, shape).numpy()
+    d = disk(host.disk_threshold(r, shape[-3:]))
+    yb, nb, _ = run(x, [d], False)
+    yg, ng, _ = run(x, [d], True)
+    ref = P.fourier_disk_mask(torch.from_numpy(x), r).numpy()
+    assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL and rel_l2(yb, yg) <= TOL
+
+
+def test_bl_is_actually_taken():
+    """5 band-limited launches (+1 min/max init), and none of the general kernels' event kinds."""
+    x = P.synthetic_volume(1, (2, 16, 12, 8)).numpy()
+    L = emu.lib()
+    plan = emu.Plan((16, 12, 8), 4)
+    B.check(L, L.mvtb_plan_profile(plan.h, 1))
+    y = np.empty_like(x)
+    d = disk(host.disk_threshold(2.5, (16, 12, 8)))
+    B.check(L, L.mvtb_kspace_chain_f32(plan.h, emu.ptr(x), emu.ptr(y), 2, host.desc_array([d]), 1, None, 1, None))
+    import ctypes as C
+    ms, cn = (C.c_double * B.K_KINDS)(), (C.c_int * B.K_KINDS)()
+    B.check(L, L.mvtb_plan_profile_read(plan.h, ms, cn))
+    kinds = {L.mvtb_kernel_name(k).decode(): cn[k] for k in range(B.K_KINDS) if cn[k]}
+    assert kinds == {"k_bl_fwd_h": 1, "k_bl_fwd_w": 1, "k_bl_mid": 1, "k_bl_inv_w": 1, "k_bl_inv_h": 1}
+
+
+def test_bl_spikes_wrap_per_volume_descs_and_minmax():
+    shape = (3, 20, 18, 15)
+    x = P.synthetic_volume(2, shape).numpy()
+    thr = host.disk_threshold(3.2, shape[-3:])
+    amp = host.exp_f32(6.0)
+    descs = [disk(thr, spikes=[((11, 10, 8), amp)], wrap_alpha=0.5),                               # inside the ball
+             disk(thr, spikes=[((2, 15, 1), amp), ((10, 9, 7), 0.5 * amp)], wrap_alpha=0.25),      # plane wave + DC bin
+             disk(thr, spikes=[((0, 0, 0), amp), ((13, 9, 7), amp)])]                              # Nyquist corner + in box, outside ball
+    yb, nb, mb = run(x, descs, False, vps=1)
+    yg, ng, mg = run(x, descs, True, vps=1)
+    for i in range(3):
+        assert rel_l2(yb[i], yg[i]) <= TOL
+        assert mb[2 * i] == yb[i].min() and mb[2 * i + 1] == yb[i].max()
+    assert np.allclose(mb, mg, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", golden_names("chain127_"))
+def test_bl_chain127_golden(name):
+    m, z = load_golden(name)
+    x = z["x"]
+    thr = host.disk_threshold(m["r"], x.shape[-3:])
+    amp = host.exp_f32(m["intensity"])
+    d = disk(thr, spikes=[(m["idx"], amp)], wrap_alpha=m["alpha"])
+    yb, nb, _ = run(x, [d], False)
+    yg, ng, _ = run(x, [d], True)
+    assert rel_l2(yb, yg) <= TOL                   # identical treatment of the zeroed-bin phase in both paths
+    if m["spike_in_ball"]:
+        assert rel_l2(yb, z["y3"]) <= TOL
+
+
+def test_bl_many_volumes_chunked_workspace():
+    shape = (11, 14, 12, 9)
+    x = P.synthetic_volume(3, shape).numpy()
+    thr = host.disk_threshold(2.2, shape[-3:])
+    descs = [disk(thr, spikes=[((i % 14, (3 * i) % 12, (5 * i) % 9), 50.0 + i)]) for i in range(11)]
+    yb, _, mb = run(x, descs, False, chunk=1, vps=4)
+    yg, _, mg = run(x, descs, True, chunk=1, vps=4)
+    assert rel_l2(yb, yg) <= TOL
+    assert np.allclose(mb, mg, rtol=1e-5, atol=1e-6)

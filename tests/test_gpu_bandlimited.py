@@ -1,0 +1,96 @@
+"""Band-limited (pruned-DFT) path on the GPU: same numbers as the general FFT path and the oracle.
+Both paths are reached through the same C-ABI call; mvtb_plan_set_path forces the general one."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def chain(x, descs, general, **kw):
+    from mvtb import _lib, functional as Fn
+    nvol = int(np.prod(x.shape[:-3]))
+    plan = Fn.get_plan(tuple(x.shape[-3:]), nvol, x.device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_set_path(plan, 1 if general else 0))
+    try:
+        return Fn.kspace_chain(x, 3, descs, **kw)
+    finally:
+        _lib.check(L, L.mvtb_plan_set_path(plan, 0))
+
+
+def disk(thr, **kw):
+    from mvtb import _lib, host
+    return host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, **kw)
+
+
+@pytest.mark.parametrize("shape,r", [((1, 240, 240, 155), 12.5), ((2, 128, 128, 64), 12.5), ((1, 128, 128, 64), 9.0),
+                                     ((1, 240, 240, 155), 15.0), ((4, 31, 45, 27), 3.5), ((1, 64, 48, 155), 2.0)])
+def test_bl_vs_oracle_and_general(cuda_device, shape, r):
+    from mvtb import host
+    from oracle import ref_port as P
+    x = P.synthetic_volume(11, shape)
+    d = disk(host.disk_threshold(r, shape[-3:]))
+    yb = chain(x.to(cuda_device), [d], False).cpu().numpy()
+    yg = chain(x.to(cuda_device), [d], True).cpu().numpy()
+    ref = P.fourier_disk_mask(x, r, False).numpy()
+    assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL and rel_l2(yb, yg) <= TOL
+
+
+def test_bl_kernels_are_the_ones_launched(cuda_device):
+    import ctypes as C
+    from mvtb import _lib, functional as Fn, host
+    x = torch.randn(2, 128, 128, 64, device=cuda_device)
+    plan = Fn.get_plan((128, 128, 64), 2, cuda_device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    Fn.kspace_chain(x, 3, [disk(host.disk_threshold(12.5, (128, 128, 64)))])
+    torch.cuda.synchronize()
+    ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
+    assert kinds == {"k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h"}
+
+
+def test_bl_chain127_full_size_out_of_ball_spike(cuda_device):
+    """The 127-chain at 240x240x155 with the spike on the (55,55,30) shell, i.e. on a bin the disk zeroed.
+    Both paths define angle(0) = 0 there and must agree; against the reference (whose phase is rounding
+    noise) the comparison is modulo that plane wave, with its amplitude checked."""
+    from mvtb import host
+    from oracle import ref_port as P
+    from test_gpu_parity import _remove_plane_wave
+    shape = (1, 240, 240, 155)
+    x = P.synthetic_volume(0, shape)
+    shell = host.ellipsoid_shell(shape[1:], 55., 55., 30.)
+    idx = tuple(int(v) for v in shell[np.random.RandomState(0).randint(0, len(shell))])
+    d = disk(host.disk_threshold(12.5, shape[1:]), spikes=[(idx, host.exp_f32(15.0))], wrap_alpha=0.5)
+    yb, mm = chain(x.to(cuda_device), [d], False, want_minmax=True)
+    yg = chain(x.to(cuda_device), [d], True)
+    assert rel_l2(yb.cpu().numpy(), yg.cpu().numpy()) <= TOL
+    assert float(mm[0, 0]) == float(yb.min()) and float(mm[0, 1]) == float(yb.max())
+    ref = P.chain_127(x, 12.5, idx, 15.0, 0.5, 0.0, None).numpy()
+    ra, aa = _remove_plane_wave(yb.cpu().numpy(), idx)
+    rb, ab = _remove_plane_wave(ref, idx)
+    assert rel_l2(ra, rb) <= 1e-4
+    assert np.allclose(aa, ab, rtol=1e-3)
+
+
+def test_bl_batch_per_sample_spikes_and_fused_minmax(cuda_device):
+    from mvtb import functional as Fn, host
+    from oracle import ref_port as P
+    B_ = 5
+    x = torch.stack([P.synthetic_volume(i, (1, 128, 128, 64)) for i in range(B_)]).to(cuda_device)
+    shell = host.ellipsoid_shell((128, 128, 64), 55., 55., 30.)
+    idxs = [tuple(int(v) for v in shell[np.random.RandomState(i).randint(0, len(shell))]) for i in range(B_)]
+    idxs[2] = (64 + 3, 64 - 2, 32 + 1)          # one sample with its spike inside the ball
+    y = Fn.chain127(x, r=12.5, spike_idx=idxs, intensity=15.0, alpha=0.5, p=None)
+    thr = host.disk_threshold(12.5, (128, 128, 64))
+    descs = [disk(thr, spikes=[(idxs[b], host.exp_f32(15.0))], wrap_alpha=0.5) for b in range(B_)]
+    yg = chain(x, descs, True)
+    assert rel_l2(y.cpu().numpy(), yg.cpu().numpy()) <= TOL
+    ref2 = P.chain_127(x[2].cpu(), 12.5, idxs[2], 15.0, 0.5, 0.0, None)
+    assert rel_l2(y[2].cpu().numpy(), ref2.numpy()) <= TOL
