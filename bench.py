@@ -92,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:  # noqa: BLE001
@@ -100,9 +100,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Median SM clock and active throttle reasons over the samples taken in [t0, t1] (the timed region)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -112,7 +113,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for (t, r) in self.rows if t0 is None or (t0 - 0.05 <= t <= t1 + 0.05)]
+        if not rows:
+            rows = [r for (_, r) in self.rows]
+        for r in rows:
             parts = [p.strip() for p in r.split(",")]
             if len(parts) < 7:
                 continue
@@ -215,7 +219,7 @@ def gpu_step(cfg, x, idxs, out, step):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
@@ -261,22 +265,24 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident timing
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for s in range(max(args.warmup, 3)):
         gpu_step(cfg, x, idxs, out, s)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = L.mvtb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    th0 = time.perf_counter()
     e0.record()
     for s in range(args.steps):
         gpu_step(cfg, x, idxs, out, 100 + s)
     e1.record()
     barrier()
+    th1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
     launches = int(L.mvtb_launch_count() - launches0)
-    clocks = sampler.stop()
+    clocks = sampler.stop(th0, th1)
     checksum = float(out.double().sum())
 
     # ---- per-kernel device time (cudaEvents around every launch, on the launching stream)

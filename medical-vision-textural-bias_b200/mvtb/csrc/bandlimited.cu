@@ -6,32 +6,39 @@
 // 550x more bins than survive the mask.  This path computes only the surviving ones, as pruned
 // DFTs with the symmetric-pair folding  x[h] +- x[N-h]  (cos part / sin part), in five kernels:
 //
-//   k_bl_fwd_h   x[v][H][W*D] real       -> Y[v][NF][W*D]      one thread per (w,d) column, streams the
+//   k_bl_fwd_h   x[v][H][W*D] real       -> Y[v][NF][W*D]      thread = 2 (w,d) columns; streams the
 //                                                             volume ONCE from HBM with coalesced loads
 //   k_bl_fwd_w   Y[v][NF][W][D]          -> G[v][NF][K][D]     K = 2F+1
 //   k_bl_mid     G: D-axis DFT to K bins, pointwise (mask / in-box spikes / wrap / 1/N), back
 //   k_bl_inv_w   G[v][NF][K][D]          -> Y[v][NF][W][D]
-//   k_bl_inv_h   Y                       -> out[v][H][W*D]     one thread per column, writes the volume
+//   k_bl_inv_h   Y                       -> out[v][H][W*D]     thread = 2 columns, writes the volume
 //                                                             ONCE; adds out-of-box spikes as plane waves
 //                                                              and tracks per-sample min/max
 //
 // HBM traffic is the compulsory 8 B/voxel plus ~1 B/voxel of intermediates (Y is NF/H of the
-// volume); arithmetic is ~2(2F+1) FMA per voxel pair and direction.  Results are the same
-// numbers the general path produces (same pointwise stage, pointwise.cuh), to fp32 rounding.
+// volume); arithmetic is ~(2F+1) FMA per voxel and direction.  cos/sin rows are read from shared
+// memory as 128-bit broadcasts.  Results are the same numbers the general path produces (same
+// pointwise stage, pointwise.cuh), to fp32 rounding.
 #include <math.h>
 #include <string.h>
+
+#include <vector>
 
 #include "pointwise.cuh"
 
 namespace mvtb {
 
-int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d);   // kspace_chain.cu
+int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d);                      // kspace_chain.cu
+int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream, void** dptr);   // plan.cu
 
-static const int kBlThreads = 256;
+static const int kColThreads = 256;      // H-axis kernels: 256 threads x 2 columns
+static const int kColsPerThread = 2;
+static const int kWThreads = 128;        // W-axis kernels
+static const int kMidThreads = 256;
 
 struct BlGeom {
     int H, W, D;
-    int F;                    // kept |f| <= F on every axis; NF = F+1 rows of the h half-spectrum
+    int F;                    // kept |f| <= F on every axis; NF >= F+1 rows of the h half-spectrum
     long long NC;             // W*D
     const float* tabC[3];     // [N][MVTB_BL_FT] cos(2 pi f n / N), axis 0 = D, 1 = W, 2 = H
     const float* tabS[3];
@@ -40,91 +47,155 @@ struct BlGeom {
 };
 
 struct PlaneWave { int fh, fw, fd; float amp; };      // signed frequencies, amplitude incl. wrap weight and 1/N
-struct PwPack {
-    int n[MVTB_DESC_PACK];
-    PlaneWave pw[MVTB_DESC_PACK][MVTB_BL_MAX_PW];
+struct BlVol {                                        // per-volume parameters, uploaded once per call
+    DescDev d;                                        // pointwise stage (in-box spikes only)
+    int npw;
+    int pad;
+    PlaneWave pw[MVTB_BL_MAX_PW];                     // out-of-box spikes
 };
 
-// cos / sin rows of one axis for n = 0 .. N/2 into shared memory, NFP floats per row
+template <int NF> struct BlDims {
+    static constexpr int NT = (2 * NF + 3) & ~3;      // floats per table row: (cos f, sin f) pairs, f = 0..NF-1
+};
+
+// Packed fp32 pairs: Blackwell's FFMA2 (fma.rn.f32x2) does two FMAs per issued instruction.  Every inner
+// loop below is arranged so that one operand pair is (cos f, sin f) straight out of a 128-bit shared load.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef MVTB_EMU
+    return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+    return __ffma2_rn(a, b, c);
+#endif
+}
+
+// (cos, sin) rows of one axis for n = 0 .. N/2 into shared memory, NT floats per row
 template <int NF>
-__device__ __forceinline__ void bl_load_table(float* sc, float* ss, const float* __restrict__ tabC,
+__device__ __forceinline__ void bl_load_table(float* sc, const float* __restrict__ tabC,
                                               const float* __restrict__ tabS, int N, int tid, int nthr) {
-    constexpr int NFP = (NF + 3) & ~3;
+    constexpr int NT = BlDims<NF>::NT;
     const int rows = N / 2 + 1;
-    for (int e = tid; e < rows * NFP; e += nthr) {
-        const int n = e / NFP, f = e - n * NFP;
-        sc[e] = f < NF ? __ldg(tabC + n * MVTB_BL_FT + f) : 0.f;
-        ss[e] = f < NF ? __ldg(tabS + n * MVTB_BL_FT + f) : 0.f;
+    for (int e = tid; e < rows * (NT / 2); e += nthr) {
+        const int n = e / (NT / 2), f = e - n * (NT / 2);
+        float c = 0.f, s = 0.f;
+        if (f < NF) { c = __ldg(tabC + n * MVTB_BL_FT + f); s = __ldg(tabS + n * MVTB_BL_FT + f); }
+        sc[2 * e] = c;
+        sc[2 * e + 1] = s;
     }
 }
 
+template <int NF>
+__device__ __forceinline__ void bl_row(const float* __restrict__ row, float2* cs) {
+    constexpr int NT = BlDims<NF>::NT;
+    const float4* s4 = reinterpret_cast<const float4*>(row);
+    MVTB_UNROLL
+    for (int i = 0; i < NT / 4; ++i) {
+        const float4 v = s4[i];
+        if (2 * i < NF) cs[2 * i] = make_float2(v.x, v.y);
+        if (2 * i + 1 < NF) cs[2 * i + 1] = make_float2(v.z, v.w);
+    }
+}
+
+#ifdef MVTB_EMU
+__device__ __forceinline__ float ld_stream(const float* p) { return *p; }
+__device__ __forceinline__ void st_stream(float* p, float v) { *p = v; }
+#else
+// the volume is touched exactly once: keep it from displacing the small intermediates in L2
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+#endif
+
 // ------------------------------------------------------------------ H axis forward: real -> NF complex rows
 template <int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_bl_fwd_h(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
-    constexpr int NFP = (NF + 3) & ~3;
+    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread, U = 4;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
-    float* ss = sc + (g.H / 2 + 1) * NFP;
     const int tid = threadIdx.x;
-    bl_load_table<NF>(sc, ss, g.tabC[2], g.tabS[2], g.H, tid, blockDim.x);
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], g.H, tid, blockDim.x);
     __syncthreads();
 
     const long long vol = blockIdx.x / n_cblocks;
-    const long long c = (long long)(blockIdx.x - vol * n_cblocks) * blockDim.x + tid;
-    if (c >= g.NC) return;
-    const float* xv = x + vol * g.H * g.NC + c;
-    float re[NF], im[NF];
-    const float x0 = xv[0];
+    const long long c0 = (long long)(blockIdx.x - vol * n_cblocks) * (blockDim.x * CPT) + tid;
+    const float* xv = x + vol * g.H * g.NC;
+    bool ok[CPT];
+    long long col[CPT];
     MVTB_UNROLL
-    for (int f = 0; f < NF; ++f) { re[f] = x0; im[f] = 0.f; }
+    for (int k = 0; k < CPT; ++k) {
+        col[k] = c0 + (long long)k * blockDim.x;
+        ok[k] = col[k] < g.NC;
+        if (!ok[k]) col[k] = g.NC - 1;                  // clamp: loads stay in bounds, stores are predicated
+    }
+    float2 acc[CPT][NF];                                // (re, im)
     const int H = g.H;
-    if ((H & 1) == 0) {
-        const float xn = xv[(long long)(H / 2) * g.NC];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        const float x0 = ld_stream(xv + col[k]);
+        const float xn = (H & 1) ? 0.f : ld_stream(xv + (long long)(H / 2) * g.NC + col[k]);
         MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) re[f] += (f & 1) ? -xn : xn;
+        for (int f = 0; f < NF; ++f) acc[k][f] = make_float2(x0 + ((f & 1) ? -xn : xn), 0.f);
     }
     const int npair = (H - 1) / 2;
+    const float* plo[CPT];
+    const float* phi[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) { plo[k] = xv + g.NC + col[k]; phi[k] = xv + (long long)(H - 1) * g.NC + col[k]; }
     int h = 1;
-    for (; h + 3 <= npair; h += 4) {          // 8 independent loads in flight per thread
-        float a[4], b[4];
+    for (; h + U - 1 <= npair; h += U) {                // 2*U*CPT independent coalesced loads in flight
+        float a[U][CPT], b[U][CPT];
         MVTB_UNROLL
-        for (int u = 0; u < 4; ++u) {
-            a[u] = xv[(long long)(h + u) * g.NC];
-            b[u] = xv[(long long)(H - h - u) * g.NC];
+        for (int u = 0; u < U; ++u) {
+            MVTB_UNROLL
+            for (int k = 0; k < CPT; ++k) {
+                a[u][k] = ld_stream(plo[k] + (long long)u * g.NC);
+                b[u][k] = ld_stream(phi[k] - (long long)u * g.NC);
+            }
         }
         MVTB_UNROLL
-        for (int u = 0; u < 4; ++u) {
-            const float e = a[u] + b[u], o = a[u] - b[u];
-            const float* c_ = sc + (h + u) * NFP;
-            const float* s_ = ss + (h + u) * NFP;
+        for (int k = 0; k < CPT; ++k) { plo[k] += (long long)U * g.NC; phi[k] -= (long long)U * g.NC; }
+        MVTB_UNROLL
+        for (int u = 0; u < U; ++u) {
+            float2 cs[NF];
+            bl_row<NF>(sc + (h + u) * NT, cs);
             MVTB_UNROLL
-            for (int f = 0; f < NF; ++f) { re[f] = fmaf(e, c_[f], re[f]); im[f] = fmaf(-o, s_[f], im[f]); }
+            for (int k = 0; k < CPT; ++k) {
+                const float2 eo = make_float2(a[u][k] + b[u][k], b[u][k] - a[u][k]);   // Im -= (a-b) sin
+                MVTB_UNROLL
+                for (int f = 0; f < NF; ++f) acc[k][f] = fma2(eo, cs[f], acc[k][f]);
+            }
         }
     }
     for (; h <= npair; ++h) {
-        const float a = xv[(long long)h * g.NC], b = xv[(long long)(H - h) * g.NC];
-        const float e = a + b, o = a - b;
-        const float* c_ = sc + h * NFP;
-        const float* s_ = ss + h * NFP;
+        float2 cs[NF];
+        bl_row<NF>(sc + h * NT, cs);
         MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) { re[f] = fmaf(e, c_[f], re[f]); im[f] = fmaf(-o, s_[f], im[f]); }
+        for (int k = 0; k < CPT; ++k) {
+            const float a = ld_stream(plo[k]), b = ld_stream(phi[k]);
+            plo[k] += g.NC; phi[k] -= g.NC;
+            const float2 eo = make_float2(a + b, b - a);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) acc[k][f] = fma2(eo, cs[f], acc[k][f]);
+        }
     }
-    cf* yv = Y + vol * NF * g.NC + c;
+    cf* yv = Y + vol * NF * g.NC;
     MVTB_UNROLL
-    for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC] = cmk(re[f], im[f]);
+    for (int k = 0; k < CPT; ++k) {
+        if (ok[k]) {
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC + col[k]] = acc[k][f];
+        }
+    }
 }
 
 // ------------------------------------------------------------------ W axis forward: Y[NF][W][D] -> G[NF][K][D]
 template <int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks) {
-    constexpr int NFP = (NF + 3) & ~3;
+    constexpr int NT = BlDims<NF>::NT, U = 4;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
-    float* ss = sc + (g.W / 2 + 1) * NFP;
     const int tid = threadIdx.x;
-    bl_load_table<NF>(sc, ss, g.tabC[1], g.tabS[1], g.W, tid, blockDim.x);
+    bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], g.W, tid, blockDim.x);
     __syncthreads();
 
     const int W = g.W, D = g.D, K = 2 * g.F + 1;
@@ -133,90 +204,112 @@ k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks
     if (t >= NF * D) return;
     const int fh = t / D, d = t - fh * D;
     const cf* yv = Y + ((vol * NF + fh) * (long long)W) * D + d;
-    cf P[NF], Q[NF];
-    const cf y0 = yv[0];
-    MVTB_UNROLL
-    for (int f = 0; f < NF; ++f) { P[f] = y0; Q[f] = cmk(0.f, 0.f); }
-    if ((W & 1) == 0) {
-        const cf yn = yv[(long long)(W / 2) * D];
-        MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) { P[f].x += (f & 1) ? -yn.x : yn.x; P[f].y += (f & 1) ? -yn.y : yn.y; }
-    }
-    const int npair = (W - 1) / 2;
-    for (int w = 1; w <= npair; ++w) {
-        const cf a = yv[(long long)w * D], b = yv[(long long)(W - w) * D];
-        const cf e = cadd(a, b), o = csub(a, b);
-        const float* c_ = sc + w * NFP;
-        const float* s_ = ss + w * NFP;
+    // P = sum (a+b) cos, Q = sum (a-b) sin (complex); kept as (P.x, Q.x) and (P.y, Q.y) pairs
+    float2 pqx[NF], pqy[NF];
+    {
+        const cf y0 = yv[0];
+        const cf yn = (W & 1) ? cmk(0.f, 0.f) : yv[(long long)(W / 2) * D];
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) {
-            P[f].x = fmaf(e.x, c_[f], P[f].x); P[f].y = fmaf(e.y, c_[f], P[f].y);
-            Q[f].x = fmaf(o.x, s_[f], Q[f].x); Q[f].y = fmaf(o.y, s_[f], Q[f].y);
+            pqx[f] = make_float2((f & 1) ? y0.x - yn.x : y0.x + yn.x, 0.f);
+            pqy[f] = make_float2((f & 1) ? y0.y - yn.y : y0.y + yn.y, 0.f);
         }
+    }
+    const int npair = (W - 1) / 2;
+    int w = 1;
+    for (; w + U - 1 <= npair; w += U) {
+        cf a[U], b[U];
+        MVTB_UNROLL
+        for (int u = 0; u < U; ++u) { a[u] = yv[(long long)(w + u) * D]; b[u] = yv[(long long)(W - w - u) * D]; }
+        MVTB_UNROLL
+        for (int u = 0; u < U; ++u) {
+            float2 cs[NF];
+            bl_row<NF>(sc + (w + u) * NT, cs);
+            const float2 ex = make_float2(a[u].x + b[u].x, a[u].x - b[u].x);
+            const float2 ey = make_float2(a[u].y + b[u].y, a[u].y - b[u].y);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
+        }
+    }
+    for (; w <= npair; ++w) {
+        float2 cs[NF];
+        bl_row<NF>(sc + w * NT, cs);
+        const cf a = yv[(long long)w * D], b = yv[(long long)(W - w) * D];
+        const float2 ex = make_float2(a.x + b.x, a.x - b.x);
+        const float2 ey = make_float2(a.y + b.y, a.y - b.y);
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
     }
     // X(+f) = P - iQ, X(-f) = P + iQ;  row j of G holds fw = j - F
     cf* gv = G + ((vol * NF + fh) * (long long)K) * D + d;
     MVTB_UNROLL
     for (int f = 0; f < NF; ++f) {
-        if (f > g.F) break;
-        gv[(long long)(g.F + f) * D] = cmk(P[f].x + Q[f].y, P[f].y - Q[f].x);
-        if (f > 0) gv[(long long)(g.F - f) * D] = cmk(P[f].x - Q[f].y, P[f].y + Q[f].x);
+        if (f <= g.F) {
+            gv[(long long)(g.F + f) * D] = cmk(pqx[f].x + pqy[f].y, pqy[f].x - pqx[f].y);
+            if (f > 0) gv[(long long)(g.F - f) * D] = cmk(pqx[f].x - pqy[f].y, pqy[f].x + pqx[f].y);
+        }
     }
 }
 
 // ------------------------------------------------------------------ D axis both ways + pointwise; CTA = (vol, fh)
 __global__ void __launch_bounds__(256)
-k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, DescPack pack) {
+k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
     MVTB_DYN_SMEM(smem_raw);
     const int D = g.D, K = 2 * g.F + 1, F = g.F;
-    cf* sg = (cf*)smem_raw;            // [K][D]
-    cf* sb = sg + K * D;               // [K][K]
-    cf* st = sb + K * K;               // [D] exp(-2 pi i t / D)
+    cf* sg = (cf*)smem_raw;            // [K][D]   rows of G for this (vol, fh)
+    cf* sw = sg + K * D;               // [K][D]   exp(-2 pi i fd d / D), fd = jd - F
+    cf* sb = sw + K * D;               // [K][K]   pointwise-processed bins
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int vol = blockIdx.x / NF, fh = blockIdx.x - vol * NF;
     cf* gv = G + ((long long)vol * NF + fh) * K * D;
-    for (int e = tid; e < K * D; e += nthr) sg[e] = gv[e];
-    for (int e = tid; e < D; e += nthr) st[e] = __ldg(g.twD + e);
+    for (int e = tid; e < K * D; e += nthr) {
+        sg[e] = gv[e];
+        const int jd = e / D, d = e - jd * D;
+        long long m = ((long long)(jd - F) * d) % D;
+        if (m < 0) m += D;
+        sw[e] = __ldg(g.twD + m);
+    }
     __syncthreads();
 
-    const DescDev& dsc = pack.d[pack.n == 1 ? 0 : vol];
+    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
     int shape[3];
     shape[0] = g.D; shape[1] = g.W; shape[2] = g.H;
     // B[jw][jd] = sum_d G[jw][d] exp(-2 pi i fd d / D), then the pointwise stage on that bin
     for (int o = tid; o < K * K; o += nthr) {
         const int jw = o / K, jd = o - jw * K;
-        const int fd = jd - F;
-        const int step = ((fd % D) + D) % D;
-        int idx = 0;
-        cf acc = cmk(0.f, 0.f);
         const cf* row = sg + jw * D;
-        for (int d = 0; d < D; ++d) {
-            const cf a = row[d], w = st[idx];
+        const cf* wr = sw + jd * D;
+        cf acc = cmk(0.f, 0.f), acc2 = cmk(0.f, 0.f);
+        int d = 0;
+        for (; d + 1 < D; d += 2) {
+            const cf a = row[d], w = wr[d], a2 = row[d + 1], w2 = wr[d + 1];
             acc.x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc.x));
             acc.y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc.y));
-            idx += step;
-            if (idx >= D) idx -= D;
+            acc2.x = fmaf(a2.x, w2.x, fmaf(-a2.y, w2.y, acc2.x));
+            acc2.y = fmaf(a2.x, w2.y, fmaf(a2.y, w2.x, acc2.y));
         }
+        if (d < D) {
+            const cf a = row[d], w = wr[d];
+            acc.x = fmaf(a.x, w.x, fmaf(-a.y, w.y, acc.x));
+            acc.y = fmaf(a.x, w.y, fmaf(a.y, w.x, acc.y));
+        }
+        acc = cadd(acc, acc2);
         int ish[3];
-        ish[0] = fd + D / 2;
+        ish[0] = (jd - F) + D / 2;
         ish[1] = (jw - F) + g.W / 2;
         ish[2] = fh + g.H / 2;
-        sb[o] = pointwise_bin(dsc, 3, shape, ish, acc, g.scale);
+        sb[o] = pointwise_bin(bv.d, 3, shape, ish, acc, g.scale);
     }
     __syncthreads();
     // G'[jw][d] = sum_jd B[jw][jd] exp(+2 pi i fd d / D)
     for (int o = tid; o < K * D; o += nthr) {
         const int jw = o / D, d = o - jw * D;
         const cf* brow = sb + jw * K;
-        // fd runs -F..F: start at (-F d) mod D and advance by d
-        int idx = (int)((((long long)(-F) * d) % D + D) % D);
         cf acc = cmk(0.f, 0.f);
         for (int jd = 0; jd < K; ++jd) {
-            const cf b = brow[jd], w = st[idx];          // conj(w) = exp(+...)
+            const cf b = brow[jd], w = sw[jd * D + d];           // conj(w) = exp(+...)
             acc.x = fmaf(b.x, w.x, fmaf(b.y, w.y, acc.x));
             acc.y = fmaf(b.y, w.x, fmaf(-b.x, w.y, acc.y));
-            idx += d;
-            if (idx >= D) idx -= D;
         }
         gv[o] = acc;
     }
@@ -224,14 +317,13 @@ k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, DescPack pack) {
 
 // ------------------------------------------------------------------ W axis inverse: G[NF][K][D] -> Y[NF][W][D]
 template <int NF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 k_bl_inv_w(const cf* __restrict__ G, cf* __restrict__ Y, BlGeom g, int n_tblocks) {
-    constexpr int NFP = (NF + 3) & ~3;
+    constexpr int NT = BlDims<NF>::NT;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
-    float* ss = sc + (g.W / 2 + 1) * NFP;
     const int tid = threadIdx.x;
-    bl_load_table<NF>(sc, ss, g.tabC[1], g.tabS[1], g.W, tid, blockDim.x);
+    bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], g.W, tid, blockDim.x);
     __syncthreads();
 
     const int W = g.W, D = g.D, K = 2 * g.F + 1;
@@ -240,19 +332,18 @@ k_bl_inv_w(const cf* __restrict__ G, cf* __restrict__ Y, BlGeom g, int n_tblocks
     if (t >= NF * D) return;
     const int fh = t / D, d = t - fh * D;
     const cf* gv = G + ((vol * NF + fh) * (long long)K) * D + d;
-    // S_f = G(+f) + G(-f), T_f = G(+f) - G(-f);  y[w] = P + iQ, y[W-w] = P - iQ with
-    // P = sum S_f cos, Q = sum T_f sin
-    cf S[NF], T[NF];
+    // S_f = G(+f) + G(-f), T_f = G(+f) - G(-f);  y[w] = P + iQ, y[W-w] = P - iQ,  P = sum S_f cos, Q = sum T_f sin
+    // kept as (S.x, T.x) and (S.y, T.y) pairs so that one FFMA2 with (cos, sin) updates (P, Q)
+    float2 stx[NF], sty[NF];
     MVTB_UNROLL
     for (int f = 0; f < NF; ++f) {
+        stx[f] = make_float2(0.f, 0.f);
+        sty[f] = make_float2(0.f, 0.f);
         if (f <= g.F) {
             const cf gp = gv[(long long)(g.F + f) * D];
             const cf gm = f > 0 ? gv[(long long)(g.F - f) * D] : cmk(0.f, 0.f);
-            S[f] = cadd(gp, gm);
-            T[f] = f > 0 ? csub(gp, gm) : cmk(0.f, 0.f);
-        } else {
-            S[f] = cmk(0.f, 0.f);
-            T[f] = cmk(0.f, 0.f);
+            stx[f] = make_float2(gp.x + gm.x, f > 0 ? gp.x - gm.x : 0.f);
+            sty[f] = make_float2(gp.y + gm.y, f > 0 ? gp.y - gm.y : 0.f);
         }
     }
     cf* yv = Y + ((vol * NF + fh) * (long long)W) * D + d;
@@ -260,24 +351,28 @@ k_bl_inv_w(const cf* __restrict__ G, cf* __restrict__ Y, BlGeom g, int n_tblocks
         cf s0 = cmk(0.f, 0.f), sn = cmk(0.f, 0.f);
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) {
-            s0 = cadd(s0, S[f]);
-            sn = (f & 1) ? csub(sn, S[f]) : cadd(sn, S[f]);
+            s0.x += stx[f].x; s0.y += sty[f].x;
+            sn.x += (f & 1) ? -stx[f].x : stx[f].x;
+            sn.y += (f & 1) ? -sty[f].x : sty[f].x;
         }
         yv[0] = s0;
         if ((W & 1) == 0) yv[(long long)(W / 2) * D] = sn;
     }
     const int npair = (W - 1) / 2;
     for (int w = 1; w <= npair; ++w) {
-        const float* c_ = sc + w * NFP;
-        const float* s_ = ss + w * NFP;
-        cf P = cmk(0.f, 0.f), Q = cmk(0.f, 0.f);
+        float2 cs[NF];
+        bl_row<NF>(sc + w * NT, cs);
+        float2 pqx = make_float2(0.f, 0.f), pqy = make_float2(0.f, 0.f);       // (P.x, Q.x), (P.y, Q.y)
+        float2 pqx2 = make_float2(0.f, 0.f), pqy2 = make_float2(0.f, 0.f);
         MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) {
-            P.x = fmaf(S[f].x, c_[f], P.x); P.y = fmaf(S[f].y, c_[f], P.y);
-            Q.x = fmaf(T[f].x, s_[f], Q.x); Q.y = fmaf(T[f].y, s_[f], Q.y);
+        for (int f = 0; f + 1 < NF; f += 2) {
+            pqx = fma2(stx[f], cs[f], pqx); pqy = fma2(sty[f], cs[f], pqy);
+            pqx2 = fma2(stx[f + 1], cs[f + 1], pqx2); pqy2 = fma2(sty[f + 1], cs[f + 1], pqy2);
         }
-        yv[(long long)w * D] = cmk(P.x - Q.y, P.y + Q.x);
-        yv[(long long)(W - w) * D] = cmk(P.x + Q.y, P.y - Q.x);
+        if (NF & 1) { pqx = fma2(stx[NF - 1], cs[NF - 1], pqx); pqy = fma2(sty[NF - 1], cs[NF - 1], pqy); }
+        const float Px = pqx.x + pqx2.x, Qx = pqx.y + pqx2.y, Py = pqy.x + pqy2.x, Qy = pqy.y + pqy2.y;
+        yv[(long long)w * D] = cmk(Px - Qy, Py + Qx);
+        yv[(long long)(W - w) * D] = cmk(Px + Qy, Py - Qx);
     }
 }
 
@@ -301,96 +396,115 @@ __device__ __forceinline__ void bl_unit(int f, int n, int N, float* c, float* s)
 }
 
 template <int NF>
-__global__ void __launch_bounds__(256)
-k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks, PwPack pws, int pack_shared,
-           float* __restrict__ minmax, int vols_per_sample, int vol_base) {
-    constexpr int NFP = (NF + 3) & ~3;
+__global__ void __launch_bounds__(256, 2)
+k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
+           const BlVol* __restrict__ vols, int vol_base, int shared_desc,
+           float* __restrict__ minmax, int vols_per_sample) {
+    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread;
     MVTB_DYN_SMEM(smem_raw);
     const int H = g.H;
     float* sc = (float*)smem_raw;
-    float* ss = sc + (H / 2 + 1) * NFP;
-    cf* seh = (cf*)(ss + (H / 2 + 1) * NFP);            // [MVTB_BL_MAX_PW][H/2+1] exp(+2 pi i fh h / H)
+    cf* seh = (cf*)(sc + (H / 2 + 1) * NT);             // [MVTB_BL_MAX_PW][H/2+1] exp(+2 pi i fh h / H)
     const int tid = threadIdx.x;
     const int vol = blockIdx.x / n_cblocks;
-    const int pslot = pack_shared ? 0 : vol;
-    const int npw = pws.n[pslot];
-    bl_load_table<NF>(sc, ss, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
-    for (int e = tid; e < npw * (H / 2 + 1); e += blockDim.x) {
+    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
+    const int npw = bv.npw;
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
+    for (int e = tid; e < MVTB_BL_MAX_PW * (H / 2 + 1); e += blockDim.x) {
         const int s = e / (H / 2 + 1), h = e - s * (H / 2 + 1);
-        float c_, s_;
-        bl_unit(pws.pw[pslot][s].fh, h, H, &c_, &s_);
+        float c_ = 0.f, s_ = 0.f;
+        if (s < npw) bl_unit(bv.pw[s].fh, h, H, &c_, &s_);
         seh[e] = cmk(c_, s_);
     }
     __syncthreads();
 
-    const long long c = (long long)(blockIdx.x - (long long)vol * n_cblocks) * blockDim.x + tid;
+    const long long c0 = (long long)(blockIdx.x - (long long)vol * n_cblocks) * (blockDim.x * CPT) + tid;
+    bool ok[CPT];
+    long long col[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        col[k] = c0 + (long long)k * blockDim.x;
+        ok[k] = col[k] < g.NC;
+        if (!ok[k]) col[k] = g.NC - 1;                  // duplicates a valid column: harmless for min/max
+    }
     float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
-    if (c < g.NC) {
-        const cf* yv = Y + (long long)vol * NF * g.NC + c;
-        float a[NF], b[NF];
+    float2 y2[CPT][NF];                                 // c_f (Re, Im) of the half-spectrum rows, c_0 = 1, c_f = 2
+    float2 E[CPT][MVTB_BL_MAX_PW];                      // plane waves: amp exp(+2 pi i (fw w/W + fd d/D)); 0 if unused
+    {
+        const cf* yv = Y + (long long)vol * NF * g.NC;
         MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) {
-            const cf y = yv[(long long)f * g.NC];
-            const float cfw = f == 0 ? 1.f : 2.f;
-            a[f] = cfw * y.x;
-            b[f] = cfw * y.y;
-        }
-        // per-column factor of every plane wave: amp * exp(+2 pi i (fw w / W + fd d / D))
-        cf E[MVTB_BL_MAX_PW];
-        {
-            const int w = (int)(c / g.D), d = (int)(c - (long long)w * g.D);
+        for (int k = 0; k < CPT; ++k) {
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                const cf y = yv[(long long)f * g.NC + col[k]];
+                const float cfw = f == 0 ? 1.f : 2.f;
+                y2[k][f] = make_float2(cfw * y.x, cfw * y.y);
+            }
+            const int w = (int)(col[k] / g.D), d = (int)(col[k] - (long long)w * g.D);
             MVTB_UNROLL
             for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                E[k][s] = make_float2(0.f, 0.f);
                 if (s < npw) {
                     float cw, sw, cd, sd;
-                    bl_unit(pws.pw[pslot][s].fw, w, g.W, &cw, &sw);
-                    bl_unit(pws.pw[pslot][s].fd, d, g.D, &cd, &sd);
-                    const float amp = pws.pw[pslot][s].amp;
-                    E[s] = cmk(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
-                } else {
-                    E[s] = cmk(0.f, 0.f);
+                    bl_unit(bv.pw[s].fw, w, g.W, &cw, &sw);
+                    bl_unit(bv.pw[s].fd, d, g.D, &cd, &sd);
+                    const float amp = bv.pw[s].amp;
+                    E[k][s] = make_float2(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
                 }
             }
         }
-        float* ov = out + (long long)vol * H * g.NC + c;
-        {
-            float v0 = 0.f, vn = 0.f;
-            MVTB_UNROLL
-            for (int f = 0; f < NF; ++f) { v0 += a[f]; vn += (f & 1) ? -a[f] : a[f]; }
-            MVTB_UNROLL
-            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
-                if (s < npw) {
-                    v0 += E[s].x;                               // exp(0) = 1
-                    if ((H & 1) == 0) {
-                        const cf eh = seh[s * (H / 2 + 1) + H / 2];
-                        vn += E[s].x * eh.x - E[s].y * eh.y;
-                    }
-                }
+    }
+    float* ov = out + (long long)vol * H * g.NC;
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        float v0 = 0.f, vn = 0.f;
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) { v0 += y2[k][f].x; vn += (f & 1) ? -y2[k][f].x : y2[k][f].x; }
+        MVTB_UNROLL
+        for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+            v0 += E[k][s].x;                                    // exp(0) = 1
+            if ((H & 1) == 0) {
+                const cf eh = seh[s * (H / 2 + 1) + H / 2];
+                vn += E[k][s].x * eh.x - E[k][s].y * eh.y;
             }
-            ov[0] = v0;
-            lo = fminf(lo, v0); hi = fmaxf(hi, v0);
-            if ((H & 1) == 0) { ov[(long long)(H / 2) * g.NC] = vn; lo = fminf(lo, vn); hi = fmaxf(hi, vn); }
         }
-        const int npair = (H - 1) / 2;
-        for (int h = 1; h <= npair; ++h) {
-            const float* c_ = sc + h * NFP;
-            const float* s_ = ss + h * NFP;
-            float P = 0.f, Q = 0.f;
+        lo = fminf(lo, v0); hi = fmaxf(hi, v0);
+        if (ok[k]) st_stream(ov + col[k], v0);
+        if ((H & 1) == 0) {
+            lo = fminf(lo, vn); hi = fmaxf(hi, vn);
+            if (ok[k]) st_stream(ov + (long long)(H / 2) * g.NC + col[k], vn);
+        }
+    }
+    const int npair = (H - 1) / 2;
+    float* plo[CPT];
+    float* phi[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) { plo[k] = ov + g.NC + col[k]; phi[k] = ov + (long long)(H - 1) * g.NC + col[k]; }
+    for (int h = 1; h <= npair; ++h) {
+        float2 cs[NF];
+        bl_row<NF>(sc + h * NT, cs);
+        float2 eh[MVTB_BL_MAX_PW];
+        MVTB_UNROLL
+        for (int s = 0; s < MVTB_BL_MAX_PW; ++s) eh[s] = seh[s * (H / 2 + 1) + h];
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            // (P, Q) = sum_f (a_f cos, b_f sin) + plane waves;  out[h] = P - Q, out[H-h] = P + Q
+            float2 pq = make_float2(0.f, 0.f), pq2 = make_float2(0.f, 0.f);
             MVTB_UNROLL
-            for (int f = 0; f < NF; ++f) { P = fmaf(a[f], c_[f], P); Q = fmaf(b[f], s_[f], Q); }
-            MVTB_UNROLL
-            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
-                if (s < npw) {
-                    const cf eh = seh[s * (H / 2 + 1) + h];
-                    P = fmaf(E[s].x, eh.x, P);
-                    Q = fmaf(E[s].y, eh.y, Q);
-                }
+            for (int f = 0; f + 1 < NF; f += 2) {
+                pq = fma2(y2[k][f], cs[f], pq);
+                pq2 = fma2(y2[k][f + 1], cs[f + 1], pq2);
             }
+            if (NF & 1) pq = fma2(y2[k][NF - 1], cs[NF - 1], pq);
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) pq2 = fma2(E[k][s], eh[s], pq2);
+            const float P = pq.x + pq2.x, Q = pq.y + pq2.y;
             const float v1 = P - Q, v2 = P + Q;
-            ov[(long long)h * g.NC] = v1;
-            ov[(long long)(H - h) * g.NC] = v2;
             lo = fminf(lo, fminf(v1, v2));
             hi = fmaxf(hi, fmaxf(v1, v2));
+            if (ok[k]) { st_stream(plo[k], v1); st_stream(phi[k], v2); }
+            plo[k] += g.NC;
+            phi[k] -= g.NC;
         }
     }
     if (minmax != nullptr) {
@@ -439,13 +553,14 @@ static int pick_nf(int need) {
 
 // can this call take the band-limited path?  fills *F_out
 bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, int* F_out) {
-    if (p->ndim != 3 || p->opt_path == 1 || !p->bl_tab) return false;
-    long long thr = desc[0].mask_thresh;
+    if (p->ndim != 3 || p->opt_path == MVTB_PATH_GENERAL || !p->bl_tab) return false;
+    const long long thr = desc[0].mask_thresh;
     for (int i = 0; i < n_desc; ++i) {
         const mvtb_chain_desc& d = desc[i];
         if (d.mask_kind != MVTB_MASK_DISK || d.mask_ndim != 3 || d.inside_off || d.mask_thresh < 0) return false;
         if (d.mask_thresh != thr) return false;
         if (d.wrap_naxes != 0 && d.wrap_naxes != 3) return false;
+        if (d.n_spikes < 0 || d.n_spikes > MVTB_MAX_SPIKES) return false;
     }
     const int F = isqrt_ll(thr);
     const int nf = pick_nf(F + 1);
@@ -456,7 +571,7 @@ bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, in
         for (int s = 0; s < desc[i].n_spikes; ++s) {
             bool in_box = true;
             for (int a = 0; a < 3; ++a) {
-                const int n = p->shape[2 - a];                // user order: outermost (H) first
+                const int n = p->shape[2 - a];              // user order: outermost (H) first
                 const int idx = desc[i].spikes[s].idx[a];
                 if (idx < 0 || idx >= n) return false;      // let the general path report the error
                 if (abs(idx - n / 2) > F) in_box = false;
@@ -476,6 +591,28 @@ size_t bl_workspace_per_volume(const mvtb_plan* p, int F) {
     return sizeof(cf) * (size_t)nf * (W * D + K * D);
 }
 
+// splits one user descriptor into the pointwise part (in-box spikes) and plane waves (the rest)
+static int bl_make_vol(const mvtb_plan* p, const BlGeom& g, const mvtb_chain_desc& u, BlVol* out) {
+    memset(out, 0, sizeof(*out));
+    mvtb_chain_desc inbox = u;
+    inbox.n_spikes = 0;
+    for (int s = 0; s < u.n_spikes; ++s) {
+        const int fh = u.spikes[s].idx[0] - g.H / 2, fw = u.spikes[s].idx[1] - g.W / 2, fd = u.spikes[s].idx[2] - g.D / 2;
+        if (abs(fh) <= g.F && abs(fw) <= g.F && abs(fd) <= g.F) {
+            inbox.spikes[inbox.n_spikes++] = u.spikes[s];
+        } else {
+            // that bin is masked to exactly 0, so new = amp * exp(i angle(0)) = amp (F:384-390)
+            float a = u.spikes[s].amplitude * g.scale;
+            if (u.wrap_naxes == 3)
+                for (int ax = 0; ax < 3; ++ax)
+                    if (u.spikes[s].idx[ax] & 1) a *= u.wrap_alpha;
+            PlaneWave& pw = out->pw[out->npw++];
+            pw.fh = fh; pw.fw = fw; pw.fd = fd; pw.amp = a;
+        }
+    }
+    return convert_desc(p, &inbox, &out->d);
+}
+
 template <int NF>
 static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
                   int F, float* minmax_out, int vols_per_sample, void* stream) {
@@ -489,18 +626,32 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     }
     g.twD = p->ax[0].tw;
     g.scale = (float)(1.0 / ((double)g.H * g.W * g.D));
-    constexpr int NFP = (NF + 3) & ~3;
+    constexpr int NT = BlDims<NF>::NT;
     const int K = 2 * F + 1;
+
+    // per-volume parameters -> device (one async copy per call)
+    std::vector<BlVol> hv((size_t)n_desc);
+    for (int i = 0; i < n_desc; ++i) {
+        int rc = bl_make_vol(p, g, desc[i], &hv[i]);
+        if (rc != MVTB_OK) return rc;
+    }
+    void* dvp = nullptr;
+    int rc = plan_stage_upload(p, hv.data(), hv.size() * sizeof(BlVol), stream, &dvp);
+    if (rc != MVTB_OK) return rc;
+    const BlVol* dv = (const BlVol*)dvp;
+    const int shared_desc = n_desc == 1 ? 1 : 0;
+
     const size_t per_vol = bl_workspace_per_volume(p, F);
     int chunk = (int)(p->ws_bytes / per_vol);
     if (chunk < 1) { set_error("band-limited path: workspace too small"); return MVTB_EUNSUPPORTED; }
     if (chunk > n_volumes) chunk = n_volumes;
-    const int n_cblocks = (int)((g.NC + kBlThreads - 1) / kBlThreads);
-    const int n_tblocks = (NF * g.D + kBlThreads - 1) / kBlThreads;
-    const size_t smem_h = sizeof(float) * 2 * (g.H / 2 + 1) * NFP;
-    const size_t smem_w = sizeof(float) * 2 * (g.W / 2 + 1) * NFP;
+    const int cols_per_cta = kColThreads * kColsPerThread;
+    const int n_cblocks = (int)((g.NC + cols_per_cta - 1) / cols_per_cta);
+    const int n_tblocks = (NF * g.D + kWThreads - 1) / kWThreads;
+    const size_t smem_h = sizeof(float) * (size_t)(g.H / 2 + 1) * NT;
+    const size_t smem_w = sizeof(float) * (size_t)(g.W / 2 + 1) * NT;
     const size_t smem_hi = smem_h + sizeof(cf) * MVTB_BL_MAX_PW * (g.H / 2 + 1);
-    const size_t smem_mid = sizeof(cf) * ((size_t)K * g.D + (size_t)K * K + g.D);
+    const size_t smem_mid = sizeof(cf) * ((size_t)2 * K * g.D + (size_t)K * K);
 
     for (int v0 = 0; v0 < n_volumes; v0 += chunk) {
         const int nv = n_volumes - v0 < chunk ? n_volumes - v0 : chunk;
@@ -509,65 +660,29 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
             auto kern = k_bl_fwd_h<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kBlThreads), smem_h, stream,
+            MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
                         in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
         }
         {
             ProfScope prof(p, MVTB_K_BL_FWD_W, stream);
             auto kern = k_bl_fwd_w<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kBlThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks);
+            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks);
         }
-        // per-volume descriptors travel by value, MVTB_DESC_PACK volumes per launch
-        const int sub = n_desc == 1 ? nv : MVTB_DESC_PACK;
-        for (int w0 = 0; w0 < nv; w0 += sub) {
-            const int nw = nv - w0 < sub ? nv - w0 : sub;
-            DescPack pack;
-            PwPack pws;
-            memset(&pack, 0, sizeof(pack));
-            memset(&pws, 0, sizeof(pws));
-            pack.n = n_desc == 1 ? 1 : (nw == 1 ? 1 : nw);
-            const int nslots = n_desc == 1 ? 1 : nw;
-            for (int i = 0; i < nslots; ++i) {
-                mvtb_chain_desc u = desc[n_desc == 1 ? 0 : v0 + w0 + i];
-                // out-of-box spikes become plane waves in k_bl_inv_h; in-box ones stay in the pointwise stage
-                mvtb_chain_desc inbox = u;
-                inbox.n_spikes = 0;
-                for (int s = 0; s < u.n_spikes; ++s) {
-                    const int fh = u.spikes[s].idx[0] - g.H / 2, fw = u.spikes[s].idx[1] - g.W / 2, fd = u.spikes[s].idx[2] - g.D / 2;
-                    const bool in_box = abs(fh) <= F && abs(fw) <= F && abs(fd) <= F;
-                    if (in_box) {
-                        inbox.spikes[inbox.n_spikes++] = u.spikes[s];
-                    } else {
-                        // the bin is masked to exactly 0, so new = amp * exp(i angle(0)) = amp (F:384-390)
-                        float a = u.spikes[s].amplitude * g.scale;
-                        if (u.wrap_naxes == 3)
-                            for (int ax = 0; ax < 3; ++ax)
-                                if (u.spikes[s].idx[ax] & 1) a *= u.wrap_alpha;
-                        PlaneWave& pw = pws.pw[i][pws.n[i]++];
-                        pw.fh = fh; pw.fw = fw; pw.fd = fd; pw.amp = a;
-                    }
-                }
-                int rc = convert_desc(p, &inbox, &pack.d[i]);
-                if (rc != MVTB_OK) return rc;
-            }
-            {
-                ProfScope prof(p, MVTB_K_BL_MID, stream);
-                MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(NF * nw)), dim3(kBlThreads), smem_mid, stream,
-                            G + (size_t)w0 * NF * K * g.D, g, NF, pack);
-            }
-            {
-                ProfScope prof(p, MVTB_K_BL_INV_W, stream);
-                auto kern = k_bl_inv_w<NF>;
-                MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nw)), dim3(kBlThreads), smem_w, stream,
-                            (const cf*)(G + (size_t)w0 * NF * K * g.D), Y + (size_t)w0 * NF * g.NC, g, n_tblocks);
-            }
-            {
-                ProfScope prof(p, MVTB_K_BL_INV_H, stream);
-                auto kern = k_bl_inv_h<NF>;
-                MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nw)), dim3(kBlThreads), smem_hi, stream,
-                            (const cf*)(Y + (size_t)w0 * NF * g.NC), out + (size_t)(v0 + w0) * p->vol_real, g, n_cblocks, pws,
-                            n_desc == 1 ? 1 : 0, minmax_out, minmax_out ? vols_per_sample : 1, v0 + w0);
-            }
+        {
+            ProfScope prof(p, MVTB_K_BL_MID, stream);
+            MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(nv * NF)), dim3(kMidThreads), smem_mid, stream, G, g, NF, dv, v0, shared_desc);
+        }
+        {
+            ProfScope prof(p, MVTB_K_BL_INV_W, stream);
+            auto kern = k_bl_inv_w<NF>;
+            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)G, Y, g, n_tblocks);
+        }
+        {
+            ProfScope prof(p, MVTB_K_BL_INV_H, stream);
+            auto kern = k_bl_inv_h<NF>;
+            MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_hi, stream,
+                        (const cf*)Y, out + (size_t)v0 * p->vol_real, g, n_cblocks, dv, v0, shared_desc,
+                        minmax_out, minmax_out ? vols_per_sample : 1);
         }
     }
     MVTB_CUDA(cudaGetLastError());

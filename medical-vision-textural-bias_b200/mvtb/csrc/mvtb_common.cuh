@@ -83,6 +83,7 @@ struct DescPack {
 }  // namespace mvtb
 
 #define MVTB_PROF_MAX 2048
+#define MVTB_STAGE_SLOTS 4
 #define MVTB_BL_FT 36                     // table columns: frequencies 0..35
 #define MVTB_BL_MAX_PW 2                  // out-of-box spikes per volume the inverse kernel adds as plane waves
 struct mvtb_plan {
@@ -106,6 +107,12 @@ struct mvtb_plan {
     int opt_path;
     float* bl_tab;
     size_t bl_off[3];
+    // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
+    void* stage_h[MVTB_STAGE_SLOTS];
+    void* stage_d[MVTB_STAGE_SLOTS];
+    size_t stage_cap[MVTB_STAGE_SLOTS];
+    cudaEvent_t stage_ev[MVTB_STAGE_SLOTS];
+    int stage_next;
     // measurement hooks (mvtb_plan_profile*)
     int profiling;
     int prof_n;

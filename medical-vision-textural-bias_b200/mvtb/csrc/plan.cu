@@ -57,6 +57,30 @@ static bool factorise(int n, std::vector<int>& out) {
     return (int)out.size() <= MVTB_MAX_STAGES;
 }
 
+// Copies a small host array to device memory on `stream` without blocking the host: the bytes go
+// through one of MVTB_STAGE_SLOTS pinned slots; a slot is reused only after the copy that last read
+// it has executed.  The device copy is valid for kernels enqueued on the same stream after this call.
+int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream, void** dptr) {
+    const int s = p->stage_next;
+    p->stage_next = (s + 1) % MVTB_STAGE_SLOTS;
+    if (p->stage_ev[s]) MVTB_CUDA(cudaEventSynchronize(p->stage_ev[s]));
+    if (bytes > p->stage_cap[s]) {
+        if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
+        if (p->stage_d[s]) cudaFree(p->stage_d[s]);       // cudaFree waits for work that may still read it
+        p->stage_h[s] = nullptr; p->stage_d[s] = nullptr; p->stage_cap[s] = 0;
+        size_t cap = bytes < 16384 ? 16384 : 2 * bytes;
+        MVTB_CUDA(cudaMallocHost(&p->stage_h[s], cap));
+        MVTB_CUDA(cudaMalloc(&p->stage_d[s], cap));
+        p->stage_cap[s] = cap;
+    }
+    if (!p->stage_ev[s]) MVTB_CUDA(cudaEventCreate(&p->stage_ev[s]));
+    memcpy(p->stage_h[s], src, bytes);
+    MVTB_CUDA(cudaMemcpyAsync(p->stage_d[s], p->stage_h[s], bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    MVTB_CUDA(cudaEventRecord(p->stage_ev[s], (cudaStream_t)stream));
+    *dptr = p->stage_d[s];
+    return MVTB_OK;
+}
+
 }  // namespace mvtb
 
 using namespace mvtb;
@@ -227,6 +251,11 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     if (p->ws) cudaFree(p->ws);
     if (p->table_mem) cudaFree(p->table_mem);
     if (p->bl_tab) cudaFree(p->bl_tab);
+    for (int s = 0; s < MVTB_STAGE_SLOTS; ++s) {
+        if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
+        if (p->stage_d[s]) cudaFree(p->stage_d[s]);
+        if (p->stage_ev[s]) cudaEventDestroy(p->stage_ev[s]);
+    }
     if (p->prof_ev[0])
         for (int i = 0; i < 2 * MVTB_PROF_MAX; ++i) cudaEventDestroy(p->prof_ev[i]);
     free(p);

@@ -160,6 +160,59 @@ k_salt_pepper(const float* __restrict__ in, float* __restrict__ out, size_t n_pe
     }
 }
 
+
+// Fast path: every sample is a whole number of 16-byte groups and all buffers are 16-byte aligned.
+// grid = (blocks per sample, samples): no index division; 4 independent 128-bit loads in flight per thread.
+// INPLACE (in == out): a selected voxel becomes a per-sample constant and an unselected one keeps its value,
+// so x is never read and only the selected voxels (a fraction p) are stored.
+template <bool PHILOX, bool INPLACE>
+__global__ void __launch_bounds__(256)
+k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigned groups_per_sample,
+                  const float* __restrict__ u, uint64_t seed, uint64_t offset, float p, const float* __restrict__ mm) {
+    const float ph = 0.5f * p;
+    const unsigned smp = blockIdx.y;
+    const float lo = 0.5f * __ldg(mm + 2 * smp), hi = 0.5f * __ldg(mm + 2 * smp + 1);
+    const size_t base = (size_t)smp * groups_per_sample;            // first group of this sample
+    const float4* in4 = (const float4*)in + base;
+    const float4* u4 = PHILOX ? nullptr : (const float4*)u + base;
+    float4* out4 = (float4*)out + base;
+    const unsigned nthreads = gridDim.x * blockDim.x;
+    unsigned gi = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; gi < groups_per_sample; gi += 4 * nthreads) {
+        float4 xv[4], uv[4];
+        MVTB_UNROLL
+        for (int k = 0; k < 4; ++k) {
+            const unsigned g = gi + k * nthreads;
+            if (g < groups_per_sample) {
+                if (!INPLACE) xv[k] = in4[g];
+                if (!PHILOX) uv[k] = u4[g];
+            }
+        }
+        MVTB_UNROLL
+        for (int k = 0; k < 4; ++k) {
+            const unsigned g = gi + k * nthreads;
+            if (g < groups_per_sample) {
+                float uu[4];
+                if (PHILOX) philox_group(seed, offset + base + g, uu);
+                else { uu[0] = uv[k].x; uu[1] = uv[k].y; uu[2] = uv[k].z; uu[3] = uv[k].w; }
+                if (INPLACE) {
+                    float* o = (float*)(out4 + g);
+                    MVTB_UNROLL
+                    for (int l = 0; l < 4; ++l)
+                        if (uu[l] <= p) o[l] = uu[l] <= ph ? lo : hi;
+                } else {
+                    float4 y;
+                    y.x = uu[0] <= ph ? lo : (uu[0] <= p ? hi : xv[k].x);
+                    y.y = uu[1] <= ph ? lo : (uu[1] <= p ? hi : xv[k].y);
+                    y.z = uu[2] <= ph ? lo : (uu[2] <= p ? hi : xv[k].z);
+                    y.w = uu[3] <= ph ? lo : (uu[3] <= p ? hi : xv[k].w);
+                    out4[g] = y;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ wraparound fold (all axes even)
 // One thread owns the orbit {h, h+H/2} x {w, w+W/2} x {d, d+D/2}: 8 reads, 8 writes, each
 // voxel touched exactly once.  Per axis: (y0, y1) = (c0 x0 + s c1 x1, c0 x1 + s c1 x0).
@@ -250,6 +303,24 @@ extern "C" int mvtb_salt_pepper_f32(const float* in, float* out, size_t n_per_sa
     if (!(p >= 0.f && p <= 1.f)) { set_error("salt_pepper: p=%g outside [0,1] (the caller clamps, F:444)", (double)p); return MVTB_EINVAL; }
     const size_t total = n_per_sample * (size_t)n_samples;
     if (total == 0) return MVTB_OK;
+    const bool aligned = ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)u)) & 15) == 0;
+    if (aligned && (n_per_sample & 3) == 0 && n_per_sample / 4 < 0xffffffffull && n_samples <= 65535) {
+        const unsigned gps = (unsigned)(n_per_sample / 4);
+        int per = kCapBlocks / n_samples;
+        if (per < 1) per = 1;
+        const unsigned bx = grid_for((gps + 3) / 4, 256, per);
+        const bool inplace = in == out;
+#define MVTB_SP_LAUNCH(PH, IP)                                                                                      \
+        do {                                                                                                        \
+            auto kern = k_salt_pepper_vec<PH, IP>;                                                                  \
+            MVTB_LAUNCH(kern, dim3(bx, (unsigned)n_samples), dim3(256), 0, stream, in, out, gps, u, seed, offset, p, minmax); \
+        } while (0)
+        if (u) { if (inplace) MVTB_SP_LAUNCH(false, true); else MVTB_SP_LAUNCH(false, false); }
+        else   { if (inplace) MVTB_SP_LAUNCH(true, true);  else MVTB_SP_LAUNCH(true, false); }
+#undef MVTB_SP_LAUNCH
+        MVTB_CUDA(cudaGetLastError());
+        return MVTB_OK;
+    }
     const unsigned grid = grid_for((total + 3) / 4, 256, kCapBlocks);
     if (u) {
         auto kern = k_salt_pepper<false>;
