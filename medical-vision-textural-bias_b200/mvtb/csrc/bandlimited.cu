@@ -35,6 +35,7 @@ static const int kColThreads = 256;      // H-axis kernels: 256 threads x 2 colu
 static const int kColsPerThread = 2;
 static const int kWThreads = 128;        // W-axis kernels
 static const int kMidThreads = 256;
+static const int kBlChunk = 64;          // volumes per band-limited launch (intermediates: ~4.3 MB per 240x240x155 volume)
 
 struct BlGeom {
     int H, W, D;
@@ -580,7 +581,6 @@ bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, in
         }
         if (outside > MVTB_BL_MAX_PW) return false;
     }
-    if (bl_workspace_per_volume(p, F) > p->ws_bytes) return false;
     *F_out = F;
     return true;
 }
@@ -641,10 +641,17 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     const BlVol* dv = (const BlVol*)dvp;
     const int shared_desc = n_desc == 1 ? 1 : 0;
 
+    // intermediates are ~NF/H of a volume each: keep up to kBlChunk volumes in flight so that the small
+    // W-axis / mid kernels get enough CTAs to fill the machine
     const size_t per_vol = bl_workspace_per_volume(p, F);
-    int chunk = (int)(p->ws_bytes / per_vol);
-    if (chunk < 1) { set_error("band-limited path: workspace too small"); return MVTB_EUNSUPPORTED; }
-    if (chunk > n_volumes) chunk = n_volumes;
+    int chunk = n_volumes < kBlChunk ? n_volumes : kBlChunk;
+    if (p->bl_ws_bytes < per_vol * (size_t)chunk) {
+        if (p->bl_ws) cudaFree(p->bl_ws);                // synchronises with work that may still use it
+        p->bl_ws = nullptr;
+        p->bl_ws_bytes = 0;
+        MVTB_CUDA(cudaMalloc((void**)&p->bl_ws, per_vol * (size_t)chunk));
+        p->bl_ws_bytes = per_vol * (size_t)chunk;
+    }
     const int cols_per_cta = kColThreads * kColsPerThread;
     const int n_cblocks = (int)((g.NC + cols_per_cta - 1) / cols_per_cta);
     const int n_tblocks = (NF * g.D + kWThreads - 1) / kWThreads;
@@ -655,7 +662,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
 
     for (int v0 = 0; v0 < n_volumes; v0 += chunk) {
         const int nv = n_volumes - v0 < chunk ? n_volumes - v0 : chunk;
-        cf* Y = p->ws;
+        cf* Y = p->bl_ws;
         cf* G = Y + (size_t)chunk * NF * g.NC;
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);

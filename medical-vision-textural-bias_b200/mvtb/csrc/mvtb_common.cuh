@@ -107,6 +107,8 @@ struct mvtb_plan {
     int opt_path;
     float* bl_tab;
     size_t bl_off[3];
+    mvtb::cf* bl_ws;                      // band-limited intermediates (Y, G), grown on demand
+    size_t bl_ws_bytes;
     // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
     void* stage_h[MVTB_STAGE_SLOTS];
     void* stage_d[MVTB_STAGE_SLOTS];

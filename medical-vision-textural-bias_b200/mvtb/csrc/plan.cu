@@ -251,6 +251,7 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     if (p->ws) cudaFree(p->ws);
     if (p->table_mem) cudaFree(p->table_mem);
     if (p->bl_tab) cudaFree(p->bl_tab);
+    if (p->bl_ws) cudaFree(p->bl_ws);
     for (int s = 0; s < MVTB_STAGE_SLOTS; ++s) {
         if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
         if (p->stage_d[s]) cudaFree(p->stage_d[s]);

@@ -14,8 +14,11 @@ import torch
 
 from . import _lib, host
 
-# in-flight half-spectra per plan: ~2 volumes of 240x240x155 so the workspace can stay L2-resident
-_WS_TARGET_BYTES = 80 << 20
+import os
+
+# plan workspace: ~2 half-spectra of 240x240x155 for the general path (L2-resident between its kernels);
+# the band-limited path fits ~16 volumes of intermediates in the same bytes.  MVTB_WS_MB overrides.
+_WS_TARGET_BYTES = int(os.environ.get("MVTB_WS_MB", "80")) << 20
 _plans = {}
 
 
