@@ -322,12 +322,26 @@ def main():
     roofline = None
     if dom:
         kd = kernels[dom]
+        vox = SHAPE[0] * SHAPE[1] * SHAPE[2]
         units_per_launch = vols_per_step / kd["launches_per_step"]
-        alg_bytes = BYTES_PER_VOXEL * SHAPE[0] * SHAPE[1] * SHAPE[2] * units_per_launch
+        # Bytes this kernel must move per voxel.  The chain's 8 B/voxel are split
+        # between the kernel that reads the volume once and the one that writes it once; the intermediates
+        # they exchange are NF/H of a volume.  The whole-step figure below uses the full 8 B/voxel.
+        nf = 13
+        own = {"k_bl_fwd_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_h": 4 + 8.0 * nf / SHAPE[0],
+               "k_rows_fwd": 8.0, "k_rows_inv": 8.0, "k_axis<FWD>": 8.0, "k_axis<MID>": 8.0, "k_axis<INV>": 8.0,
+               "k_salt_pepper<philox>": 8.0 if cfg["p"] is None else 4.0 * cfg["p"]}.get(dom, 8.0)
+        # DRAM bytes per volume from the ncu --set full capture of this command (profiles/r01_ncu_full_selected_metrics.csv)
+        ncu_traffic = {"k_bl_fwd_h": 39.73e6, "k_bl_inv_h": 38.72e6, "k_salt_pepper<philox>": 23.86e6}.get(dom)
+        alg_bytes = own * vox * units_per_launch
         achieved = alg_bytes / (kd["avg_launch_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                    "share_of_step": kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values())}
+                    "traffic": None if ncu_traffic is None else ncu_traffic * units_per_launch,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                    "algorithmic_bytes_per_voxel_this_kernel": own,
+                    "share_of_step": kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
+                    "chain_bytes_per_voxel": BYTES_PER_VOXEL,
+                    "chain_equivalent_frac": (BYTES_PER_VOXEL * vox * units_per_launch / (kd["avg_launch_ms"] * 1e-3) / 1e9) / peak}
 
     # ---- end to end through the public API with host buffers: every step copies the batch from pinned host
     # memory, runs the chain, and copies the result back.  The batch moves in slices so that the H2D copy of
@@ -396,7 +410,9 @@ def main():
                        "rng": "in-kernel Philox4x32-10"},
             "channel_volumes_per_s": value * C,
             "roofline": roofline,
-            "hbm_frac_whole_step": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+            "roofline_whole_step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                    "frac": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
+                                    "note": "8 B/voxel x voxels per step / step time: the figure the 60% target refers to"},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(voxels * 4), "d2h_bytes_per_step": int(voxels * 4),
                     "steps": e2e_steps, "slices_per_step": n_slices, "checksum": e2e_checksum},

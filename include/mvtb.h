@@ -138,6 +138,7 @@ unsigned long long mvtb_launch_count(void);           /* kernels launched by thi
  * result to fp32 rounding; the switch exists for tests and measurements. */
 #define MVTB_PATH_AUTO 0
 #define MVTB_PATH_GENERAL 1
+#define MVTB_PATH_BL_PAIRS 2   /* automatic, but the band-limited H kernels use pair folding even when H % 4 == 0 */
 int mvtb_plan_set_path(mvtb_plan* plan, int path);
 
 #ifdef __cplusplus

@@ -535,6 +535,8 @@ k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cb
     }
 }
 
+#include "bandlimited_quad.cuh"
+
 // ------------------------------------------------------------------ host side
 size_t bl_workspace_per_volume(const mvtb_plan* p, int F);
 
@@ -640,6 +642,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     if (rc != MVTB_OK) return rc;
     const BlVol* dv = (const BlVol*)dvp;
     const int shared_desc = n_desc == 1 ? 1 : 0;
+    const bool quad = (g.H % 4) == 0 && p->opt_quad;      // four rows per table row (bandlimited_quad.cuh)
 
     // intermediates are ~NF/H of a volume each: keep up to kBlChunk volumes in flight so that the small
     // W-axis / mid kernels get enough CTAs to fill the machine
@@ -666,7 +669,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         cf* G = Y + (size_t)chunk * NF * g.NC;
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
-            auto kern = k_bl_fwd_h<NF>;
+            auto kern = quad ? k_bl_fwd_h4<NF> : k_bl_fwd_h<NF>;
             MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
                         in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
         }
@@ -686,7 +689,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
         {
             ProfScope prof(p, MVTB_K_BL_INV_H, stream);
-            auto kern = k_bl_inv_h<NF>;
+            auto kern = quad ? k_bl_inv_h4<NF> : k_bl_inv_h<NF>;
             MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_hi, stream,
                         (const cf*)Y, out + (size_t)v0 * p->vol_real, g, n_cblocks, dv, v0, shared_desc,
                         minmax_out, minmax_out ? vols_per_sample : 1);
@@ -722,6 +725,8 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_fwd_w<NF>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_w<NF>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h<NF>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_h4<NF>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }
 #endif

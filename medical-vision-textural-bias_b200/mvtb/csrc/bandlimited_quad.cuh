@@ -1,0 +1,298 @@
+// bandlimited_quad.cuh — H-axis kernels of the band-limited path for H % 4 == 0 (240, 128, 64, ...).
+//
+// One more level of symmetry than the pair folding: rows h, H-h, H/2-h, H/2+h share
+// cos_f(h), sin_f(h) up to signs that depend only on the parity of f:
+//     cos_f(H-h) =  cos_f(h)            sin_f(H-h) = -sin_f(h)
+//     cos_f(H/2-h) = (-1)^f cos_f(h)    sin_f(H/2-h) = -(-1)^f ... = (-1)^(f+1) (-sin_f(h)) ...
+// worked out below.  Four rows are produced / consumed per table row, which halves the FMAs and the
+// shared-memory table traffic per voxel relative to k_bl_fwd_h / k_bl_inv_h.  Included by bandlimited.cu.
+// (no namespace here: included inside namespace mvtb)
+#pragma once
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+#ifdef MVTB_EMU
+    return make_float2(a.x + b.x, a.y + b.y);
+#else
+    return __fadd2_rn(a, b);
+#endif
+}
+
+// ------------------------------------------------------------------ forward, quads
+// a = x[h], b = x[H-h], c = x[H/2-h], d = x[H/2+h]:
+//   f even:  re += (a+b+c+d) cos,  im -= (a-b-c+d) sin
+//   f odd :  re += (a+b-c-d) cos,  im -= (a-b+c-d) sin
+template <int NF>
+__global__ void __launch_bounds__(256, 2)
+k_bl_fwd_h4(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
+    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread, U = 2;
+    MVTB_DYN_SMEM(smem_raw);
+    float* sc = (float*)smem_raw;
+    const int tid = threadIdx.x;
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], g.H, tid, blockDim.x);
+    __syncthreads();
+
+    const long long vol = blockIdx.x / n_cblocks;
+    const long long c0 = (long long)(blockIdx.x - vol * n_cblocks) * (blockDim.x * CPT) + tid;
+    const float* xv = x + vol * g.H * g.NC;
+    bool ok[CPT];
+    long long col[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        col[k] = c0 + (long long)k * blockDim.x;
+        ok[k] = col[k] < g.NC;
+        if (!ok[k]) col[k] = g.NC - 1;
+    }
+    const int H = g.H, H2 = H / 2, H4 = H / 4;
+    float2 acc[CPT][NF];                                // (re, im)
+    {
+        // rows 0 and H/2 (cos = 1 / (-1)^f, sin = 0), then the pair H/4, 3H/4 with table row H/4
+        float2 cs[NF];
+        bl_row<NF>(sc + H4 * NT, cs);
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            const float x0 = ld_stream(xv + col[k]);
+            const float xn = ld_stream(xv + (long long)H2 * g.NC + col[k]);
+            const float a = ld_stream(xv + (long long)H4 * g.NC + col[k]);
+            const float b = ld_stream(xv + (long long)(H - H4) * g.NC + col[k]);
+            const float2 eo = make_float2(a + b, b - a);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) acc[k][f] = fma2(eo, cs[f], make_float2(x0 + ((f & 1) ? -xn : xn), 0.f));
+        }
+    }
+    const float* pa[CPT];   // row h        (ascending)
+    const float* pb[CPT];   // row H-h      (descending)
+    const float* pc[CPT];   // row H/2-h    (descending)
+    const float* pd[CPT];   // row H/2+h    (ascending)
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        pa[k] = xv + g.NC + col[k];
+        pb[k] = xv + (long long)(H - 1) * g.NC + col[k];
+        pc[k] = xv + (long long)(H2 - 1) * g.NC + col[k];
+        pd[k] = xv + (long long)(H2 + 1) * g.NC + col[k];
+    }
+    const int nq = H4 - 1;
+    int h = 1;
+    for (; h + U - 1 <= nq; h += U) {                   // 4*U*CPT independent coalesced loads in flight
+        float a[U][CPT], b[U][CPT], c[U][CPT], d[U][CPT];
+        MVTB_UNROLL
+        for (int u = 0; u < U; ++u) {
+            MVTB_UNROLL
+            for (int k = 0; k < CPT; ++k) {
+                a[u][k] = ld_stream(pa[k] + (long long)u * g.NC);
+                b[u][k] = ld_stream(pb[k] - (long long)u * g.NC);
+                c[u][k] = ld_stream(pc[k] - (long long)u * g.NC);
+                d[u][k] = ld_stream(pd[k] + (long long)u * g.NC);
+            }
+        }
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            pa[k] += (long long)U * g.NC; pd[k] += (long long)U * g.NC;
+            pb[k] -= (long long)U * g.NC; pc[k] -= (long long)U * g.NC;
+        }
+        MVTB_UNROLL
+        for (int u = 0; u < U; ++u) {
+            float2 cs[NF];
+            bl_row<NF>(sc + (h + u) * NT, cs);
+            MVTB_UNROLL
+            for (int k = 0; k < CPT; ++k) {
+                const float s1 = a[u][k] + b[u][k], s2 = c[u][k] + d[u][k];
+                const float d1 = a[u][k] - b[u][k], d2 = c[u][k] - d[u][k];
+                const float2 ev = make_float2(s1 + s2, d2 - d1);        // (ee, -oe),  oe = d1 - d2
+                const float2 od = make_float2(s1 - s2, -(d1 + d2));     // (eo, -oo),  oo = d1 + d2
+                MVTB_UNROLL
+                for (int f = 0; f < NF; ++f) acc[k][f] = fma2((f & 1) ? od : ev, cs[f], acc[k][f]);
+            }
+        }
+    }
+    for (; h <= nq; ++h) {
+        float2 cs[NF];
+        bl_row<NF>(sc + h * NT, cs);
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            const float a = ld_stream(pa[k]), b = ld_stream(pb[k]), c = ld_stream(pc[k]), d = ld_stream(pd[k]);
+            pa[k] += g.NC; pd[k] += g.NC; pb[k] -= g.NC; pc[k] -= g.NC;
+            const float s1 = a + b, s2 = c + d, d1 = a - b, d2 = c - d;
+            const float2 ev = make_float2(s1 + s2, d2 - d1);
+            const float2 od = make_float2(s1 - s2, -(d1 + d2));
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) acc[k][f] = fma2((f & 1) ? od : ev, cs[f], acc[k][f]);
+        }
+    }
+    cf* yv = Y + vol * NF * g.NC;
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        if (ok[k]) {
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC + col[k]] = acc[k][f];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ inverse, quads
+// With (Pe, Qe) = sum over even f of (a_f cos_f(h), b_f sin_f(h)) and (Po, Qo) over odd f:
+//   out[h]     = (Pe+Po) - (Qe+Qo)        out[H-h]   = (Pe+Po) + (Qe+Qo)
+//   out[H/2-h] = (Pe-Po) + (Qe-Qo)        out[H/2+h] = (Pe-Po) - (Qe-Qo)
+// A plane wave with frequency f_s joins the even or the odd sums according to the parity of f_s.
+template <int NF>
+__global__ void __launch_bounds__(256, 2)
+k_bl_inv_h4(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
+            const BlVol* __restrict__ vols, int vol_base, int shared_desc,
+            float* __restrict__ minmax, int vols_per_sample) {
+    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread;
+    MVTB_DYN_SMEM(smem_raw);
+    const int H = g.H, H2 = H / 2, H4 = H / 4;
+    float* sc = (float*)smem_raw;
+    cf* seh = (cf*)(sc + (H2 + 1) * NT);                // [MVTB_BL_MAX_PW][H/2+1] exp(+2 pi i fh h / H)
+    const int tid = threadIdx.x;
+    const int vol = blockIdx.x / n_cblocks;
+    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
+    const int npw = bv.npw;
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
+    for (int e = tid; e < MVTB_BL_MAX_PW * (H2 + 1); e += blockDim.x) {
+        const int s = e / (H2 + 1), h = e - s * (H2 + 1);
+        float c_ = 0.f, s_ = 0.f;
+        if (s < npw) bl_unit(bv.pw[s].fh, h, H, &c_, &s_);
+        seh[e] = cmk(c_, s_);
+    }
+    __syncthreads();
+    bool podd[MVTB_BL_MAX_PW];
+    MVTB_UNROLL
+    for (int s = 0; s < MVTB_BL_MAX_PW; ++s) podd[s] = s < npw && (bv.pw[s].fh & 1);
+
+    const long long c0 = (long long)(blockIdx.x - (long long)vol * n_cblocks) * (blockDim.x * CPT) + tid;
+    bool ok[CPT];
+    long long col[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        col[k] = c0 + (long long)k * blockDim.x;
+        ok[k] = col[k] < g.NC;
+        if (!ok[k]) col[k] = g.NC - 1;
+    }
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
+    float2 y2[CPT][NF];
+    float2 E[CPT][MVTB_BL_MAX_PW];
+    {
+        const cf* yv = Y + (long long)vol * NF * g.NC;
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                const cf y = yv[(long long)f * g.NC + col[k]];
+                const float cfw = f == 0 ? 1.f : 2.f;
+                y2[k][f] = make_float2(cfw * y.x, cfw * y.y);
+            }
+            const int w = (int)(col[k] / g.D), d = (int)(col[k] - (long long)w * g.D);
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                E[k][s] = make_float2(0.f, 0.f);
+                if (s < npw) {
+                    float cw, sw, cd, sd;
+                    bl_unit(bv.pw[s].fw, w, g.W, &cw, &sw);
+                    bl_unit(bv.pw[s].fd, d, g.D, &cd, &sd);
+                    const float amp = bv.pw[s].amp;
+                    E[k][s] = make_float2(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
+                }
+            }
+        }
+    }
+    float* ov = out + (long long)vol * H * g.NC;
+    // rows 0, H/2 and the pair H/4, 3H/4
+    {
+        float2 cs[NF];
+        bl_row<NF>(sc + H4 * NT, cs);
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            float v0 = 0.f, vn = 0.f;
+            float2 pq = make_float2(0.f, 0.f);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                v0 += y2[k][f].x;
+                vn += (f & 1) ? -y2[k][f].x : y2[k][f].x;
+                pq = fma2(y2[k][f], cs[f], pq);
+            }
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                const cf e2 = seh[s * (H2 + 1) + H2], e4 = seh[s * (H2 + 1) + H4];
+                v0 += E[k][s].x;
+                vn += E[k][s].x * e2.x - E[k][s].y * e2.y;
+                pq = fma2(E[k][s], e4, pq);
+            }
+            const float vq = pq.x - pq.y, v3q = pq.x + pq.y;
+            lo = fminf(fminf(lo, v0), fminf(vn, fminf(vq, v3q)));
+            hi = fmaxf(fmaxf(hi, v0), fmaxf(vn, fmaxf(vq, v3q)));
+            if (ok[k]) {
+                st_stream(ov + col[k], v0);
+                st_stream(ov + (long long)H2 * g.NC + col[k], vn);
+                st_stream(ov + (long long)H4 * g.NC + col[k], vq);
+                st_stream(ov + (long long)(H - H4) * g.NC + col[k], v3q);
+            }
+        }
+    }
+    float* pa[CPT];
+    float* pb[CPT];
+    float* pc[CPT];
+    float* pd[CPT];
+    MVTB_UNROLL
+    for (int k = 0; k < CPT; ++k) {
+        pa[k] = ov + g.NC + col[k];
+        pb[k] = ov + (long long)(H - 1) * g.NC + col[k];
+        pc[k] = ov + (long long)(H2 - 1) * g.NC + col[k];
+        pd[k] = ov + (long long)(H2 + 1) * g.NC + col[k];
+    }
+    const int nq = H4 - 1;
+    for (int h = 1; h <= nq; ++h) {
+        float2 cs[NF];
+        bl_row<NF>(sc + h * NT, cs);
+        float2 eh[MVTB_BL_MAX_PW];
+        MVTB_UNROLL
+        for (int s = 0; s < MVTB_BL_MAX_PW; ++s) eh[s] = seh[s * (H2 + 1) + h];
+        MVTB_UNROLL
+        for (int k = 0; k < CPT; ++k) {
+            float2 pe = make_float2(0.f, 0.f), po = make_float2(0.f, 0.f);       // (Pe, Qe), (Po, Qo)
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                if (f & 1) po = fma2(y2[k][f], cs[f], po);
+                else pe = fma2(y2[k][f], cs[f], pe);
+            }
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                if (podd[s]) po = fma2(E[k][s], eh[s], po);
+                else pe = fma2(E[k][s], eh[s], pe);
+            }
+            const float2 sm = add2(pe, po);                                       // (Pe+Po, Qe+Qo)
+            const float2 df = add2(pe, make_float2(-po.x, -po.y));                // (Pe-Po, Qe-Qo)
+            const float v1 = sm.x - sm.y, v2 = sm.x + sm.y, v3 = df.x + df.y, v4 = df.x - df.y;
+            lo = fminf(fminf(lo, fminf(v1, v2)), fminf(v3, v4));
+            hi = fmaxf(fmaxf(hi, fmaxf(v1, v2)), fmaxf(v3, v4));
+            if (ok[k]) { st_stream(pa[k], v1); st_stream(pb[k], v2); st_stream(pc[k], v3); st_stream(pd[k], v4); }
+            pa[k] += g.NC; pd[k] += g.NC;
+            pb[k] -= g.NC; pc[k] -= g.NC;
+        }
+    }
+    if (minmax != nullptr) {
+        __shared__ float s_lo[32], s_hi[32];
+        MVTB_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        const int lane = tid & 31, wp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane == 0) { s_lo[wp] = lo; s_hi[wp] = hi; }
+        __syncthreads();
+        if (wp == 0) {
+            lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+            hi = lane < nw ? s_hi[lane] : __int_as_float((int)0xff800000u);
+            MVTB_UNROLL
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) {
+                float* mm = minmax + 2 * ((vol_base + vol) / vols_per_sample);
+                bl_atomic_min(mm, lo);
+                bl_atomic_max(mm + 1, hi);
+            }
+        }
+    }
+}
+

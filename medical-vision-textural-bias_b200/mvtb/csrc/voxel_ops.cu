@@ -173,6 +173,10 @@ k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigne
     const unsigned smp = blockIdx.y;
     const float lo = 0.5f * __ldg(mm + 2 * smp), hi = 0.5f * __ldg(mm + 2 * smp + 1);
     const size_t base = (size_t)smp * groups_per_sample;            // first group of this sample
+    // integer thresholds on the raw 32-bit Philox words (p, ph in [0,1]; p 2^24 is exact in fp32)
+    const unsigned kp = (unsigned)(p * 16777216.0f), kph = (unsigned)(ph * 16777216.0f);
+    const unsigned tp = kp >= 16777216u ? 0xffffffffu : ((kp << 8) | 0xffu);
+    const unsigned tph = kph >= 16777216u ? 0xffffffffu : ((kph << 8) | 0xffu);
     const float4* in4 = (const float4*)in + base;
     const float4* u4 = PHILOX ? nullptr : (const float4*)u + base;
     float4* out4 = (float4*)out + base;
@@ -192,6 +196,21 @@ k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigne
         for (int k = 0; k < 4; ++k) {
             const unsigned g = gi + k * nthreads;
             if (g < groups_per_sample) {
+                if (PHILOX && INPLACE) {
+                    // u = k 2^-24 with k = r >> 8, so  u <= p  <=>  r <= (floor(p 2^24) << 8 | 0xff): integer compares,
+                    // no int->float conversion; bit-identical to the float comparison
+                    uint4 c = make_uint4((unsigned)(offset + base + g), (unsigned)((offset + base + g) >> 32), 0u, 0u);
+                    uint2 key;
+                    key.x = (unsigned)seed;
+                    key.y = (unsigned)(seed >> 32);
+                    const uint4 r = Philox::run(c, key);
+                    float* o = (float*)(out4 + g);
+                    if (r.x <= tp) o[0] = r.x <= tph ? lo : hi;
+                    if (r.y <= tp) o[1] = r.y <= tph ? lo : hi;
+                    if (r.z <= tp) o[2] = r.z <= tph ? lo : hi;
+                    if (r.w <= tp) o[3] = r.w <= tph ? lo : hi;
+                    continue;
+                }
                 float uu[4];
                 if (PHILOX) philox_group(seed, offset + base + g, uu);
                 else { uu[0] = uv[k].x; uu[1] = uv[k].y; uu[2] = uv[k].z; uu[3] = uv[k].w; }

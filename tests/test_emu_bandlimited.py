@@ -93,6 +93,27 @@ def test_bl_chain127_golden(name):
         assert rel_l2(yb, z["y3"]) <= TOL
 
 
+def test_bl_quad_symmetry_kernels_match_pair_kernels():
+    """H % 4 == 0 uses the four-rows-per-table-row kernels; MVTB_PATH_BL_PAIRS (2) forces the pair kernels."""
+    shape = (2, 24, 14, 11)
+    x = P.synthetic_volume(4, shape).numpy()
+    thr = host.disk_threshold(3.3, shape[-3:])
+    amp = host.exp_f32(5.0)
+    descs = [disk(thr, spikes=[((3, 9, 2), amp), ((20, 1, 10), amp)], wrap_alpha=0.5),     # odd and even f_h plane waves
+             disk(thr, spikes=[((12, 7, 5), amp)])]
+    L = emu.lib()
+    outs = []
+    for path in (0, 2, 1):
+        plan = emu.Plan(shape[-3:], 4)
+        B.check(L, L.mvtb_plan_set_path(plan.h, path))
+        y = np.empty_like(x)
+        mm = np.zeros(4, dtype=np.float32)
+        B.check(L, L.mvtb_kspace_chain_f32(plan.h, emu.ptr(x), emu.ptr(y), 2, host.desc_array(descs), 2, emu.ptr(mm), 1, None))
+        outs.append((y, mm))
+    assert rel_l2(outs[0][0], outs[1][0]) <= TOL and rel_l2(outs[0][0], outs[2][0]) <= TOL
+    assert np.allclose(outs[0][1], outs[2][1], rtol=1e-5, atol=1e-6)
+
+
 def test_bl_many_volumes_chunked_workspace():
     shape = (11, 14, 12, 9)
     x = P.synthetic_volume(3, shape).numpy()
