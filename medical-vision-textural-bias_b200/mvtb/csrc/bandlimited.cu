@@ -20,6 +20,7 @@
 // memory as 128-bit broadcasts.  Results are the same numbers the general path produces (same
 // pointwise stage, pointwise.cuh), to fp32 rounding.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -34,6 +35,7 @@ int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream,
 static const int kColThreads = 256;      // H-axis kernels: 256 threads x 2 columns
 static const int kColsPerThread = 2;
 static const int kWThreads = 128;        // W-axis kernels
+static const int kWParts = 4;            // lanes per (fh, d) column in k_bl_fwd_w
 static const int kMidThreads = 256;
 static const int kBlChunk = 64;          // volumes per band-limited launch (intermediates: ~4.3 MB per 240x240x155 volume)
 
@@ -189,10 +191,12 @@ k_bl_fwd_h(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblo
 }
 
 // ------------------------------------------------------------------ W axis forward: Y[NF][W][D] -> G[NF][K][D]
+// kWParts lanes share one (fh, d) column (w-pairs interleaved among them, xor-shuffle reduction at the end):
+// 4x the threads of a thread-per-column mapping, which this latency-bound kernel needs to fill the machine.
 template <int NF>
 __global__ void __launch_bounds__(128)
 k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks) {
-    constexpr int NT = BlDims<NF>::NT, U = 4;
+    constexpr int NT = BlDims<NF>::NT, PARTS = kWParts;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
     const int tid = threadIdx.x;
@@ -201,15 +205,21 @@ k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks
 
     const int W = g.W, D = g.D, K = 2 * g.F + 1;
     const long long vol = blockIdx.x / n_tblocks;
-    const int t = (int)(blockIdx.x - vol * n_tblocks) * blockDim.x + tid;     // (fh, d)
-    if (t >= NF * D) return;
-    const int fh = t / D, d = t - fh * D;
+    const int t = (int)(blockIdx.x - vol * n_tblocks) * blockDim.x + tid;
+    int q = t / PARTS;                                   // (fh, d)
+    const int part = t - q * PARTS;
+    const bool valid = q < NF * D;
+    if (!valid) q = NF * D - 1;                          // keep the lane in the shuffles
+    const int fh = q / D, d = q - fh * D;
     const cf* yv = Y + ((vol * NF + fh) * (long long)W) * D + d;
     // P = sum (a+b) cos, Q = sum (a-b) sin (complex); kept as (P.x, Q.x) and (P.y, Q.y) pairs
     float2 pqx[NF], pqy[NF];
     {
-        const cf y0 = yv[0];
-        const cf yn = (W & 1) ? cmk(0.f, 0.f) : yv[(long long)(W / 2) * D];
+        cf y0 = cmk(0.f, 0.f), yn = cmk(0.f, 0.f);
+        if (part == 0) {
+            y0 = yv[0];
+            if ((W & 1) == 0) yn = yv[(long long)(W / 2) * D];
+        }
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) {
             pqx[f] = make_float2((f & 1) ? y0.x - yn.x : y0.x + yn.x, 0.f);
@@ -217,35 +227,44 @@ k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks
         }
     }
     const int npair = (W - 1) / 2;
-    int w = 1;
-    for (; w + U - 1 <= npair; w += U) {
-        cf a[U], b[U];
-        MVTB_UNROLL
-        for (int u = 0; u < U; ++u) { a[u] = yv[(long long)(w + u) * D]; b[u] = yv[(long long)(W - w - u) * D]; }
-        MVTB_UNROLL
-        for (int u = 0; u < U; ++u) {
-            float2 cs[NF];
-            bl_row<NF>(sc + (w + u) * NT, cs);
-            const float2 ex = make_float2(a[u].x + b[u].x, a[u].x - b[u].x);
-            const float2 ey = make_float2(a[u].y + b[u].y, a[u].y - b[u].y);
-            MVTB_UNROLL
-            for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
-        }
-    }
-    for (; w <= npair; ++w) {
+    int w = 1 + part;
+    for (; w + PARTS <= npair; w += 2 * PARTS) {         // two pairs (four 8-byte loads) in flight
+        const cf a0 = yv[(long long)w * D], b0 = yv[(long long)(W - w) * D];
+        const cf a1 = yv[(long long)(w + PARTS) * D], b1 = yv[(long long)(W - w - PARTS) * D];
         float2 cs[NF];
         bl_row<NF>(sc + w * NT, cs);
-        const cf a = yv[(long long)w * D], b = yv[(long long)(W - w) * D];
-        const float2 ex = make_float2(a.x + b.x, a.x - b.x);
-        const float2 ey = make_float2(a.y + b.y, a.y - b.y);
+        float2 ex = make_float2(a0.x + b0.x, a0.x - b0.x), ey = make_float2(a0.y + b0.y, a0.y - b0.y);
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
+        bl_row<NF>(sc + (w + PARTS) * NT, cs);
+        ex = make_float2(a1.x + b1.x, a1.x - b1.x);
+        ey = make_float2(a1.y + b1.y, a1.y - b1.y);
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
     }
-    // X(+f) = P - iQ, X(-f) = P + iQ;  row j of G holds fw = j - F
+    for (; w <= npair; w += PARTS) {
+        float2 cs[NF];
+        bl_row<NF>(sc + w * NT, cs);
+        const cf a = yv[(long long)w * D], b = yv[(long long)(W - w) * D];
+        const float2 ex = make_float2(a.x + b.x, a.x - b.x), ey = make_float2(a.y + b.y, a.y - b.y);
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
+    }
+    MVTB_UNROLL
+    for (int f = 0; f < NF; ++f) {
+        MVTB_UNROLL
+        for (int o = 1; o < PARTS; o <<= 1) {
+            pqx[f].x += __shfl_xor_sync(0xffffffffu, pqx[f].x, o);
+            pqx[f].y += __shfl_xor_sync(0xffffffffu, pqx[f].y, o);
+            pqy[f].x += __shfl_xor_sync(0xffffffffu, pqy[f].x, o);
+            pqy[f].y += __shfl_xor_sync(0xffffffffu, pqy[f].y, o);
+        }
+    }
+    // X(+f) = P - iQ, X(-f) = P + iQ;  row j of G holds fw = j - F; the PARTS lanes share the stores
     cf* gv = G + ((vol * NF + fh) * (long long)K) * D + d;
     MVTB_UNROLL
     for (int f = 0; f < NF; ++f) {
-        if (f <= g.F) {
+        if (valid && f <= g.F && (f % PARTS) == part) {
             gv[(long long)(g.F + f) * D] = cmk(pqx[f].x + pqy[f].y, pqy[f].x - pqx[f].y);
             if (f > 0) gv[(long long)(g.F - f) * D] = cmk(pqx[f].x - pqy[f].y, pqy[f].x + pqx[f].y);
         }
@@ -254,7 +273,8 @@ k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks
 
 // ------------------------------------------------------------------ D axis both ways + pointwise; CTA = (vol, fh)
 __global__ void __launch_bounds__(256)
-k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
+k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, const BlVol* __restrict__ vols, int vol_base, int shared_desc,
+         const cf* __restrict__ twkd /* [K][D] exp(-2 pi i (jd-F) d / D) */) {
     MVTB_DYN_SMEM(smem_raw);
     const int D = g.D, K = 2 * g.F + 1, F = g.F;
     cf* sg = (cf*)smem_raw;            // [K][D]   rows of G for this (vol, fh)
@@ -265,10 +285,7 @@ k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, const BlVol* __restrict__ vols, i
     cf* gv = G + ((long long)vol * NF + fh) * K * D;
     for (int e = tid; e < K * D; e += nthr) {
         sg[e] = gv[e];
-        const int jd = e / D, d = e - jd * D;
-        long long m = ((long long)(jd - F) * d) % D;
-        if (m < 0) m += D;
-        sw[e] = __ldg(g.twD + m);
+        sw[e] = __ldg(twkd + e);
     }
     __syncthreads();
 
@@ -637,10 +654,26 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         int rc = bl_make_vol(p, g, desc[i], &hv[i]);
         if (rc != MVTB_OK) return rc;
     }
+    // ... followed by the [K][D] D-axis twiddle table of the mid kernel
+    const size_t vol_bytes = (hv.size() * sizeof(BlVol) + 15) & ~(size_t)15;
+    std::vector<unsigned char> hbuf(vol_bytes + sizeof(cf) * (size_t)K * g.D);
+    memcpy(hbuf.data(), hv.data(), hv.size() * sizeof(BlVol));
+    {
+        cf* tw = (cf*)(hbuf.data() + vol_bytes);
+        for (int jd = 0; jd < K; ++jd)
+            for (int d = 0; d < g.D; ++d) {
+                long long m = ((long long)(jd - F) * d) % g.D;
+                if (m < 0) m += g.D;
+                const double ang = -2.0 * M_PI * (double)m / (double)g.D;
+                tw[(size_t)jd * g.D + d].x = (float)cos(ang);
+                tw[(size_t)jd * g.D + d].y = (float)sin(ang);
+            }
+    }
     void* dvp = nullptr;
-    int rc = plan_stage_upload(p, hv.data(), hv.size() * sizeof(BlVol), stream, &dvp);
+    int rc = plan_stage_upload(p, hbuf.data(), hbuf.size(), stream, &dvp);
     if (rc != MVTB_OK) return rc;
     const BlVol* dv = (const BlVol*)dvp;
+    const cf* dtw = (const cf*)((const unsigned char*)dvp + vol_bytes);
     const int shared_desc = n_desc == 1 ? 1 : 0;
     const bool quad = (g.H % 4) == 0 && p->opt_quad;      // four rows per table row (bandlimited_quad.cuh)
 
@@ -658,6 +691,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     const int cols_per_cta = kColThreads * kColsPerThread;
     const int n_cblocks = (int)((g.NC + cols_per_cta - 1) / cols_per_cta);
     const int n_tblocks = (NF * g.D + kWThreads - 1) / kWThreads;
+    const int n_tblocks_f = (NF * g.D * kWParts + kWThreads - 1) / kWThreads;
     const size_t smem_h = sizeof(float) * (size_t)(g.H / 2 + 1) * NT;
     const size_t smem_w = sizeof(float) * (size_t)(g.W / 2 + 1) * NT;
     const size_t smem_hi = smem_h + sizeof(cf) * MVTB_BL_MAX_PW * (g.H / 2 + 1);
@@ -669,18 +703,27 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         cf* G = Y + (size_t)chunk * NF * g.NC;
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
-            auto kern = quad ? k_bl_fwd_h4<NF> : k_bl_fwd_h<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
-                        in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
+            if (quad) {
+                const int variant = getenv("MVTB_FWD_VARIANT") ? atoi(getenv("MVTB_FWD_VARIANT")) : 1;
+                const int ncb1 = (int)((g.NC + kColThreads - 1) / kColThreads);
+                if (variant == 1) { auto kern = k_bl_fwd_h4<NF, 1, 4, 3>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
+                else if (variant == 2) { auto kern = k_bl_fwd_h4<NF, 1, 8, 2>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
+                else if (variant == 3) { auto kern = k_bl_fwd_h4<NF, 1, 2, 4>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
+                else { auto kern = k_bl_fwd_h4<NF, 2, 2, 2>; MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, n_cblocks); }
+            } else {
+                auto kern = k_bl_fwd_h<NF>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
+                            in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
+            }
         }
         {
             ProfScope prof(p, MVTB_K_BL_FWD_W, stream);
             auto kern = k_bl_fwd_w<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks);
+            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks_f * nv)), dim3(kWThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks_f);
         }
         {
             ProfScope prof(p, MVTB_K_BL_MID, stream);
-            MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(nv * NF)), dim3(kMidThreads), smem_mid, stream, G, g, NF, dv, v0, shared_desc);
+            MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(nv * NF)), dim3(kMidThreads), smem_mid, stream, G, g, NF, dv, v0, shared_desc, dtw);
         }
         {
             ProfScope prof(p, MVTB_K_BL_INV_W, stream);
@@ -725,7 +768,10 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_fwd_w<NF>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_w<NF>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h<NF>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h4<NF>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 2, 2, 2>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, 3>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 8, 2>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 2, 4>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h4<NF>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }

@@ -21,10 +21,10 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 // a = x[h], b = x[H-h], c = x[H/2-h], d = x[H/2+h]:
 //   f even:  re += (a+b+c+d) cos,  im -= (a-b-c+d) sin
 //   f odd :  re += (a+b-c-d) cos,  im -= (a-b+c-d) sin
-template <int NF>
-__global__ void __launch_bounds__(256, 2)
+template <int NF, int CPT, int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_bl_fwd_h4(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
-    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread, U = 2;
+    constexpr int NT = BlDims<NF>::NT;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
     const int tid = threadIdx.x;

@@ -151,39 +151,54 @@ __device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_str
     }
 }
 
-template <bool INV, bool SEQ_FAST>
+// MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all).  The radix-31
+// butterfly alone needs > 128 registers, so kernels for axes without big primes are instantiated without it.
+template <bool INV, bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stride, int elem_stride, int count,
                                                    int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
     switch (R) {
 #define MVTB_CASE(RR) case RR: fft_stage<RR, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
-        MVTB_CASE(2) MVTB_CASE(3) MVTB_CASE(4) MVTB_CASE(5) MVTB_CASE(7) MVTB_CASE(11) MVTB_CASE(13)
-        MVTB_CASE(17) MVTB_CASE(19) MVTB_CASE(23) MVTB_CASE(29) MVTB_CASE(31)
+        MVTB_CASE(2) MVTB_CASE(3) MVTB_CASE(4) MVTB_CASE(5)
+        default:
+            if (MAXR > 5) {
+                switch (R) {
+                    MVTB_CASE(7) MVTB_CASE(11) MVTB_CASE(13)
+                    default:
+                        if (MAXR > 13) {
+                            switch (R) {
+                                MVTB_CASE(17) MVTB_CASE(19) MVTB_CASE(23) MVTB_CASE(29) MVTB_CASE(31)
+                                default: break;
+                            }
+                        }
+                        break;
+                }
+            }
+            break;
 #undef MVTB_CASE
-        default: break;
     }
 }
 
 // Whole transform; the caller has synchronised before, and a __syncthreads() follows every stage.
-template <bool SEQ_FAST>
+template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr) {
     int L = ax.n;
     for (int s = 0; s < ax.nstage; ++s) {
         const int R = ax.radix[s];
-        fft_stage_dispatch<false, SEQ_FAST>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
         L /= R;
         __syncthreads();
     }
 }
 
-template <bool SEQ_FAST>
+template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr) {
     int L = 1;
     for (int s = ax.nstage - 1; s >= 0; --s) {
         const int R = ax.radix[s];
         L *= R;
-        fft_stage_dispatch<true, SEQ_FAST>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
         __syncthreads();
     }
 }

@@ -81,7 +81,10 @@ __device__ __forceinline__ void block_minmax_commit(float lo, float hi, float* m
 }
 
 // ------------------------------------------------------------------ axis 0: real rows <-> half spectrum
-__global__ void __launch_bounds__(256)
+#define MVTB_MINB(MAXR) ((MAXR) <= 5 ? 3 : ((MAXR) <= 13 ? 2 : 1))
+
+template <int MAXR>
+__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
 k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh, int pitch,
            int pairs_per_cta, long long n_rows) {
     MVTB_DYN_SMEM(smem_raw);
@@ -100,7 +103,7 @@ k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh
         s[rp * pitch + j] = cmk(a, b);
     }
     __syncthreads();
-    fft_forward<false>(ax, s, pitch, 1, np, tid, nthr);
+    fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr);
 
     // Z = FFT(a + i b):  A[k] = (Z[k] + conj Z[n-k]) / 2,  B[k] = (Z[k] - conj Z[n-k]) / (2i)
     for (int e = tid; e < np * nh; e += nthr) {
@@ -114,7 +117,8 @@ k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh
     }
 }
 
-__global__ void __launch_bounds__(256)
+template <int MAXR>
+__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
 k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int nh, int pitch,
            int pairs_per_cta, long long n_rows, float* __restrict__ minmax, long long rows_per_sample,
            long long row_base) {
@@ -136,7 +140,7 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
         if (k != 0 && 2 * k != n) s[rp * pitch + __ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
     }
     __syncthreads();
-    fft_inverse<false>(ax, s, pitch, 1, np, tid, nthr);
+    fft_inverse<false, MAXR>(ax, s, pitch, 1, np, tid, nthr);
 
     float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
     const long long row_first = 2 * pair0;
@@ -182,8 +186,8 @@ __device__ __forceinline__ cf spike_value(cf ko, float amp) {
 
 // Axes >= 1 of the half-spectrum workspace, viewed as [outer][n][inner].
 // One CTA owns a tile of T adjacent `inner` columns over the whole axis: shared memory [n][T].
-template <int MODE>
-__global__ void __launch_bounds__(256)
+template <int MODE, int MAXR>
+__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
 k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int ntiles,
        ChainGeom g, DescPack pack, double* __restrict__ sums) {
     MVTB_DYN_SMEM(smem_raw);
@@ -201,7 +205,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     }
     __syncthreads();
 
-    if (MODE != AX_INV) fft_forward<true>(ax, s, 1, T, T, tid, nthr);
+    if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr);
 
     if (MODE == AX_MID) {
         const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
@@ -310,7 +314,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
         return;
     }
 
-    if (MODE != AX_FWD) fft_inverse<true>(ax, s, 1, T, T, tid, nthr);
+    if (MODE != AX_FWD) fft_inverse<true, MAXR>(ax, s, 1, T, T, tid, nthr);
 
     for (int e = tid; e < n * T; e += nthr) {
         const int j = e / T;
@@ -329,21 +333,41 @@ static int allow_big_smem(K kern, int optin) {
 }
 #endif
 
+template <int MAXR>
+static int configure_maxr(int optin) {
+#ifndef MVTB_EMU
+    int rc;
+    if ((rc = allow_big_smem(k_rows_fwd<MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_rows_inv<MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_FWD, MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_INV, MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_MID, MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_axis<AX_STATS, MAXR>, optin)) != MVTB_OK) return rc;
+#endif
+    (void)optin;
+    return MVTB_OK;
+}
+
 int configure_chain_kernels(const mvtb_plan* p) {
+    int optin = 0;
 #ifndef MVTB_EMU
     cudaDeviceProp prop;
     MVTB_CUDA(cudaGetDeviceProperties(&prop, p->device));
-    const int optin = (int)prop.sharedMemPerBlockOptin;
-    int rc;
-    if ((rc = allow_big_smem(k_rows_fwd, optin)) != MVTB_OK) return rc;
-    if ((rc = allow_big_smem(k_rows_inv, optin)) != MVTB_OK) return rc;
-    if ((rc = allow_big_smem(k_axis<AX_FWD>, optin)) != MVTB_OK) return rc;
-    if ((rc = allow_big_smem(k_axis<AX_INV>, optin)) != MVTB_OK) return rc;
-    if ((rc = allow_big_smem(k_axis<AX_MID>, optin)) != MVTB_OK) return rc;
-    if ((rc = allow_big_smem(k_axis<AX_STATS>, optin)) != MVTB_OK) return rc;
+    optin = (int)prop.sharedMemPerBlockOptin;
 #endif
     (void)p;
+    int rc;
+    if ((rc = configure_maxr<5>(optin)) != MVTB_OK) return rc;
+    if ((rc = configure_maxr<13>(optin)) != MVTB_OK) return rc;
+    if ((rc = configure_maxr<31>(optin)) != MVTB_OK) return rc;
     return MVTB_OK;
+}
+
+// radix class of an axis: which kernel instantiation can run it
+static int axis_maxr(const mvtb_plan* p, int a) {
+    int m = 2;
+    for (int s = 0; s < p->ax[a].nstage; ++s) m = p->ax[a].radix[s] > m ? p->ax[a].radix[s] : m;
+    return m <= 5 ? 5 : (m <= 13 ? 13 : 31);
 }
 
 static ChainGeom make_geom(const mvtb_plan* p) {
@@ -404,7 +428,11 @@ static int launch_rows_fwd(mvtb_plan* p, const float* in, cf* ws, long long n_ro
     const int rp = p->rows_pairs_per_cta;
     const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
     const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
-    MVTB_LAUNCH(k_rows_fwd, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows);
+    switch (axis_maxr(p, 0)) {
+        case 5: { auto kern = k_rows_fwd<5>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows); break; }
+        case 13: { auto kern = k_rows_fwd<13>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows); break; }
+        default: { auto kern = k_rows_fwd<31>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows); break; }
+    }
     return MVTB_OK;
 }
 
@@ -421,8 +449,11 @@ static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const C
     const long long blocks = ntiles * outer;
     if (blocks > 0x7fffffffLL) { set_error("chain: grid too large"); return MVTB_EUNSUPPORTED; }
     const size_t smem = (size_t)p->shape[axis] * T * sizeof(cf);
-    auto kern = k_axis<MODE>;
-    MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums);
+    switch (axis_maxr(p, axis)) {
+        case 5: { auto kern = k_axis<MODE, 5>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
+        case 13: { auto kern = k_axis<MODE, 13>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
+        default: { auto kern = k_axis<MODE, 31>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
+    }
     return MVTB_OK;
 }
 
@@ -503,9 +534,19 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
             const long long rows_per_sample = rows_per_vol * (minmax_out ? vols_per_sample : 1);
             // chunks need not align with samples: the kernel works from the global row number
             ProfScope prof(p, MVTB_K_ROWS_INV, stream);
-            MVTB_LAUNCH(k_rows_inv, dim3(grid), dim3(kThreads), smem, stream, (const cf*)p->ws,
-                        out + (size_t)v0 * p->vol_real, p->ax[0], p->nh, p->row_pitch, rp, n_rows,
-                        minmax_out, rows_per_sample, rows_per_vol * (long long)v0);
+#define MVTB_ROWS_INV(MAXR)                                                                                   \
+            do {                                                                                              \
+                auto kern = k_rows_inv<MAXR>;                                                                 \
+                MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, (const cf*)p->ws,                 \
+                            out + (size_t)v0 * p->vol_real, p->ax[0], p->nh, p->row_pitch, rp, n_rows,        \
+                            minmax_out, rows_per_sample, rows_per_vol * (long long)v0);                       \
+            } while (0)
+            switch (axis_maxr(p, 0)) {
+                case 5: MVTB_ROWS_INV(5); break;
+                case 13: MVTB_ROWS_INV(13); break;
+                default: MVTB_ROWS_INV(31); break;
+            }
+#undef MVTB_ROWS_INV
         }
     }
     MVTB_CUDA(cudaGetLastError());

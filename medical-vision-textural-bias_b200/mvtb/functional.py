@@ -70,6 +70,8 @@ def get_plan(fft_shape: Sequence[int], n_volumes: int, dev: torch.device):
         h = C.c_void_p()
         shp = (C.c_int * len(fft_shape))(*fft_shape)
         _lib.check(L, L.mvtb_plan_create(C.byref(h), len(fft_shape), shp, chunk, dev.index))
+        if os.environ.get("MVTB_PATH"):              # measurements: 1 = general FFT path only, 2 = pair kernels
+            _lib.check(L, L.mvtb_plan_set_path(h, int(os.environ["MVTB_PATH"])))
         _plans[key] = h
     return h
 
