@@ -33,7 +33,8 @@ int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d);     
 int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream, void** dptr);   // plan.cu
 
 static const int kColThreads = 256;      // H-axis kernels: 256 threads x 2 columns
-static const int kColsPerThread = 2;
+// columns per thread in the H-axis kernels: 2 while the accumulators fit (NF <= 16), else 1
+template <int NF> struct BlCols { static constexpr int CPT = NF > 16 ? 1 : 2; };
 static const int kWThreads = 128;        // W-axis kernels
 static const int kWParts = 4;            // lanes per (fh, d) column in k_bl_fwd_w
 static const int kMidThreads = 256;
@@ -108,10 +109,10 @@ __device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
 #endif
 
 // ------------------------------------------------------------------ H axis forward: real -> NF complex rows
-template <int NF>
+template <int NF, int CPT>
 __global__ void __launch_bounds__(256, 2)
 k_bl_fwd_h(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
-    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread, U = 4;
+    constexpr int NT = BlDims<NF>::NT, U = 4;
     MVTB_DYN_SMEM(smem_raw);
     float* sc = (float*)smem_raw;
     const int tid = threadIdx.x;
@@ -194,7 +195,7 @@ k_bl_fwd_h(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblo
 // kWParts lanes share one (fh, d) column (w-pairs interleaved among them, xor-shuffle reduction at the end):
 // 4x the threads of a thread-per-column mapping, which this latency-bound kernel needs to fill the machine.
 template <int NF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (NF > 16 ? 2 : 4))
 k_bl_fwd_w(const cf* __restrict__ Y, cf* __restrict__ G, BlGeom g, int n_tblocks) {
     constexpr int NT = BlDims<NF>::NT, PARTS = kWParts;
     MVTB_DYN_SMEM(smem_raw);
@@ -335,7 +336,7 @@ k_bl_mid(cf* __restrict__ G, BlGeom g, int NF, const BlVol* __restrict__ vols, i
 
 // ------------------------------------------------------------------ W axis inverse: G[NF][K][D] -> Y[NF][W][D]
 template <int NF>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (NF > 16 ? 2 : 4))
 k_bl_inv_w(const cf* __restrict__ G, cf* __restrict__ Y, BlGeom g, int n_tblocks) {
     constexpr int NT = BlDims<NF>::NT;
     MVTB_DYN_SMEM(smem_raw);
@@ -413,12 +414,12 @@ __device__ __forceinline__ void bl_unit(int f, int n, int N, float* c, float* s)
     sincospif(2.0f * (float)m / (float)N, s, c);
 }
 
-template <int NF>
+template <int NF, int CPT>
 __global__ void __launch_bounds__(256, 2)
 k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
            const BlVol* __restrict__ vols, int vol_base, int shared_desc,
            float* __restrict__ minmax, int vols_per_sample) {
-    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread;
+    constexpr int NT = BlDims<NF>::NT;
     MVTB_DYN_SMEM(smem_raw);
     const int H = g.H;
     float* sc = (float*)smem_raw;
@@ -565,7 +566,7 @@ static int isqrt_ll(long long v) {
 }
 
 static int pick_nf(int need) {
-    static const int avail[] = {4, 8, 13, 16};
+    static const int avail[] = {4, 8, 13, 16, 20, 26, 32};
     for (int a : avail)
         if (need <= a) return a;
     return 0;
@@ -688,7 +689,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         MVTB_CUDA(cudaMalloc((void**)&p->bl_ws, per_vol * (size_t)chunk));
         p->bl_ws_bytes = per_vol * (size_t)chunk;
     }
-    const int cols_per_cta = kColThreads * kColsPerThread;
+    constexpr int CPT = BlCols<NF>::CPT;
+    const int cols_per_cta = kColThreads * CPT;
     const int n_cblocks = (int)((g.NC + cols_per_cta - 1) / cols_per_cta);
     const int n_tblocks = (NF * g.D + kWThreads - 1) / kWThreads;
     const int n_tblocks_f = (NF * g.D * kWParts + kWThreads - 1) / kWThreads;
@@ -704,14 +706,12 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
             if (quad) {
-                const int variant = getenv("MVTB_FWD_VARIANT") ? atoi(getenv("MVTB_FWD_VARIANT")) : 1;
+                // one column per thread, 16 loads in flight, 3 CTAs/SM while the accumulators allow (measured best)
                 const int ncb1 = (int)((g.NC + kColThreads - 1) / kColThreads);
-                if (variant == 1) { auto kern = k_bl_fwd_h4<NF, 1, 4, 3>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
-                else if (variant == 2) { auto kern = k_bl_fwd_h4<NF, 1, 8, 2>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
-                else if (variant == 3) { auto kern = k_bl_fwd_h4<NF, 1, 2, 4>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1); }
-                else { auto kern = k_bl_fwd_h4<NF, 2, 2, 2>; MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, n_cblocks); }
+                auto kern = k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1);
             } else {
-                auto kern = k_bl_fwd_h<NF>;
+                auto kern = k_bl_fwd_h<NF, CPT>;
                 MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
                             in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
             }
@@ -732,7 +732,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
         {
             ProfScope prof(p, MVTB_K_BL_INV_H, stream);
-            auto kern = quad ? k_bl_inv_h4<NF> : k_bl_inv_h<NF>;
+            auto kern = quad ? k_bl_inv_h4<NF, CPT> : k_bl_inv_h<NF, CPT>;
             MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_hi, stream,
                         (const cf*)Y, out + (size_t)v0 * p->vol_real, g, n_cblocks, dv, v0, shared_desc,
                         minmax_out, minmax_out ? vols_per_sample : 1);
@@ -749,6 +749,9 @@ int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvt
         case 8: return bl_run<8>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
         case 13: return bl_run<13>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
         case 16: return bl_run<16>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
+        case 20: return bl_run<20>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
+        case 26: return bl_run<26>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
+        case 32: return bl_run<32>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
         default: set_error("band-limited path: F=%d not instantiated", F); return MVTB_EUNSUPPORTED;
     }
 }
@@ -763,16 +766,14 @@ static int bl_big_smem(K kern, int optin) {
 }
 template <int NF>
 static int bl_configure_nf(int optin) {
+    constexpr int CPT = BlCols<NF>::CPT;
     int rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h<NF>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h<NF, CPT>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_fwd_w<NF>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_w<NF>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_inv_h<NF>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 2, 2, 2>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, 3>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 8, 2>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 2, 4>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_inv_h4<NF>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_h<NF, CPT>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }
 #endif
@@ -787,6 +788,9 @@ int configure_bl_kernels(const mvtb_plan* p) {
     if ((rc = bl_configure_nf<8>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_configure_nf<13>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_configure_nf<16>(optin)) != MVTB_OK) return rc;
+    if ((rc = bl_configure_nf<20>(optin)) != MVTB_OK) return rc;
+    if ((rc = bl_configure_nf<26>(optin)) != MVTB_OK) return rc;
+    if ((rc = bl_configure_nf<32>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_mid, optin)) != MVTB_OK) return rc;
 #endif
     (void)p;

@@ -133,12 +133,12 @@ k_bl_fwd_h4(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cbl
 //   out[h]     = (Pe+Po) - (Qe+Qo)        out[H-h]   = (Pe+Po) + (Qe+Qo)
 //   out[H/2-h] = (Pe-Po) + (Qe-Qo)        out[H/2+h] = (Pe-Po) - (Qe-Qo)
 // A plane wave with frequency f_s joins the even or the odd sums according to the parity of f_s.
-template <int NF>
+template <int NF, int CPT>
 __global__ void __launch_bounds__(256, 2)
 k_bl_inv_h4(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
             const BlVol* __restrict__ vols, int vol_base, int shared_desc,
             float* __restrict__ minmax, int vols_per_sample) {
-    constexpr int NT = BlDims<NF>::NT, CPT = kColsPerThread;
+    constexpr int NT = BlDims<NF>::NT;
     MVTB_DYN_SMEM(smem_raw);
     const int H = g.H, H2 = H / 2, H4 = H / 4;
     float* sc = (float*)smem_raw;

@@ -37,7 +37,8 @@ def disk(thr, **kw):
 
 
 @pytest.mark.parametrize("shape,r", [((2, 16, 12, 8), 2.5), ((1, 32, 32, 16), 4.0), ((1, 9, 15, 25), 2.5),
-                                     ((3, 12, 10, 31), 3.0), ((1, 30, 26, 27), 12.5)])
+                                     ((3, 12, 10, 31), 3.0), ((1, 30, 26, 27), 12.5), ((1, 44, 40, 39), 18.5),
+                                     ((1, 64, 51, 52), 25.0), ((1, 63, 64, 65), 30.5)])
 def test_bl_matches_oracle_and_general(shape, r):
     x = P.synthetic_volume(1, shape).numpy()
     d = disk(host.disk_threshold(r, shape[-3:]))

@@ -28,7 +28,8 @@ def disk(thr, **kw):
 
 
 @pytest.mark.parametrize("shape,r", [((1, 240, 240, 155), 12.5), ((2, 128, 128, 64), 12.5), ((1, 128, 128, 64), 9.0),
-                                     ((1, 240, 240, 155), 15.0), ((4, 31, 45, 27), 3.5), ((1, 64, 48, 155), 2.0)])
+                                     ((1, 240, 240, 155), 15.0), ((4, 31, 45, 27), 3.5), ((1, 64, 48, 155), 2.0),
+                                     ((1, 240, 240, 155), 20.0), ((1, 128, 128, 64), 25.0), ((1, 240, 240, 155), 30.0)])
 def test_bl_vs_oracle_and_general(cuda_device, shape, r):
     from mvtb import host
     from oracle import ref_port as P
