@@ -34,6 +34,9 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 SHAPE = (240, 240, 155)
+# in-kernel S&P sampler: one Philox uniform per voxel (default; 7.9 us/vol) or the geometric-gap sampler
+# (MVTB_SPARSE_SP=1; fewer instructions but its per-thread scattered stores cost 15 us/vol on B200)
+SPARSE_SP = os.environ.get("MVTB_SPARSE_SP", "0") == "1"
 BYTES_PER_VOXEL = 8            # algorithmic: read fp32 once + write fp32 once
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -215,6 +218,10 @@ def gpu_step(cfg, x, idxs, out, step, group_offset=None):
     if cfg["p"] is None:
         return Fn.kspace_chain(x, 3, descs, out=out)
     y, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C, out=out)
+    if SPARSE_SP:                                   # geometric-gap Bernoulli sampler: counters count 256-voxel blocks
+        nb = B * ((x.numel() // B + 255) // 256)
+        off = step * nb if group_offset is None else group_offset // 64
+        return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=off, n_samples=B, mm=mm, out=y, sparse=True)
     n4 = (x.numel() + 3) // 4
     off = step * n4 if group_offset is None else group_offset
     return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=off, n_samples=B, mm=mm, out=y)
@@ -313,7 +320,7 @@ def main():
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for s in range(3):
-            Fn2.salt_pepper(out, cfg["p"], seed=1, offset=0, n_samples=B, mm=mm, out=out)
+            Fn2.salt_pepper(out, cfg["p"], seed=1, offset=0, n_samples=B, mm=mm, out=out, sparse=SPARSE_SP)
         b.record()
         torch.cuda.synchronize(dev)
         kernels["k_salt_pepper<philox>"] = {"launches_per_step": 1, "ms_per_step": a.elapsed_time(b) / 3, "avg_launch_ms": a.elapsed_time(b) / 3}
@@ -407,7 +414,7 @@ def main():
             "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % C, "samples_per_gpu": B,
                        "volumes_per_step_per_gpu": vols_per_step, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs larger than L2 (%.2f GB in + out per step per GPU)" % (2 * voxels * 4 / 1e9),
-                       "rng": "in-kernel Philox4x32-10"},
+                       "rng": "in-kernel Philox4x32-10, " + ("geometric-gap Bernoulli sampler (cost ~ p)" if SPARSE_SP else "one uniform per voxel")},
             "channel_volumes_per_s": value * C,
             "roofline": roofline,
             "roofline_whole_step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -106,6 +106,18 @@ int mvtb_salt_pepper_f32(const float* in, float* out, size_t n_per_sample, int n
                          const float* u, uint64_t seed, uint64_t offset, float p,
                          const float* minmax, void* stream);
 
+/* In-place salt-and-pepper whose cost is proportional to p: instead of one uniform per voxel, each block of
+ * MVTB_SP_BLOCK consecutive voxels of a sample is walked from hit to hit with geometric gaps drawn from
+ * Philox4x32-10 by inverse CDF against the integer table of mvtb_sparse_table (exact integer compares), plus
+ * one random bit for salt vs pepper.  The voxels hit are i.i.d. Bernoulli(p) exactly as with `u <= p`, and
+ * half of them get min/2, half max/2 (F:478-479).  Deterministic in (seed, offset, p); a different random
+ * field than mvtb_salt_pepper_f32's.  table_dev: device scratch of MVTB_SP_BLOCK uint32 owned by the caller. */
+#define MVTB_SP_BLOCK 256
+int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset,
+                                float p, const float* minmax, unsigned* table_dev, void* stream);
+/* T[k] = floor(2^32 (1 - (1-p)^(k+1))), k < MVTB_SP_BLOCK (host memory) */
+int mvtb_sparse_table(float p, unsigned* table_out);
+
 /* the uniforms mvtb_salt_pepper_f32 uses when u == NULL (for tests and for feeding the oracle) */
 int mvtb_philox_uniform_f32(float* out, size_t n, uint64_t seed, uint64_t offset, void* stream);
 

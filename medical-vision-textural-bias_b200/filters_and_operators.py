@@ -258,15 +258,17 @@ class SaltAndPepper(MapTransform, RandomizableTransform):
 
     rng="torch" (default) draws u with torch.rand on the CPU generator exactly where the reference does
     (F:472), so seeded runs reproduce it bit for bit; rng="philox" draws u inside the kernel from
-    Philox4x32-10 keyed by `seed` (counter advances every call) and never touches host memory."""
+    Philox4x32-10 keyed by `seed` (counter advances every call) and never touches host memory;
+    rng="philox-sparse" walks from hit to hit with Philox-drawn geometric gaps (same Bernoulli(p) field
+    statistics, cost proportional to p)."""
 
     def __init__(self, p: float = 0, keys: Union[str, List['str']] = 'image', prob: float = 1.,
                  allow_missing_keys: bool = False, *, rng: str = "torch", seed: int = 0):
         self.p = min(max(0, p), 1.)
         if p < 0 or p > 1:
             warnings.warn(f'Setting p to {self.p}.')
-        if rng not in ("torch", "philox"):
-            raise ValueError("rng must be 'torch' or 'philox'")
+        if rng not in ("torch", "philox", "philox-sparse"):
+            raise ValueError("rng must be 'torch', 'philox' or 'philox-sparse'")
         self.rng = rng
         self.seed = int(seed)
         self.offset = 0
@@ -290,9 +292,10 @@ class SaltAndPepper(MapTransform, RandomizableTransform):
         ud = None
         if u is not None:
             ud = u.to(device=xd.device, dtype=torch.float32).contiguous()
-        y = Fn.salt_pepper(xd, float(self.p), u=ud, seed=self.seed, offset=self.offset, n_samples=1)
+        sparse = ud is None and self.rng == "philox-sparse"
+        y = Fn.salt_pepper(xd, float(self.p), u=ud, seed=self.seed, offset=self.offset, n_samples=1, sparse=sparse)
         if ud is None:
-            self.offset += (xd.numel() + 3) // 4
+            self.offset += (xd.numel() + 255) // 256 if sparse else (xd.numel() + 3) // 4
         return Fn.back(y, src)
 
 

@@ -50,6 +50,9 @@ _SYMBOLS = {
     "mvtb_minmax_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_salt_pepper_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
                                        C.c_float, C.c_void_p, C.c_void_p]),
+    "mvtb_salt_pepper_sparse_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_uint64, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvtb_sparse_table": (C.c_int, [C.c_float, C.POINTER(C.c_uint32)]),
     "mvtb_philox_uniform_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mvtb_wrap_fold_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "mvtb_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
@@ -59,6 +62,7 @@ _SYMBOLS = {
     "mvtb_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
 }
 K_KINDS = 16
+SP_BLOCK = 256
 
 
 def bind(cdll):

@@ -732,10 +732,18 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
         {
             ProfScope prof(p, MVTB_K_BL_INV_H, stream);
-            auto kern = quad ? k_bl_inv_h4<NF, CPT> : k_bl_inv_h<NF, CPT>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_hi, stream,
-                        (const cf*)Y, out + (size_t)v0 * p->vol_real, g, n_cblocks, dv, v0, shared_desc,
-                        minmax_out, minmax_out ? vols_per_sample : 1);
+            if (quad && CPT == 2 && (g.NC % 2) == 0 && g.NC * (long long)g.H < 0x7fffffffLL && (((uintptr_t)out) & 7) == 0) {
+                const int ncb2 = (int)((g.NC / 2 + kColThreads - 1) / kColThreads);
+                auto kern = k_bl_inv_h4v<NF>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(ncb2 * nv)), dim3(kColThreads), smem_hi, stream,
+                            (const cf*)Y, out + (size_t)v0 * p->vol_real, g, ncb2, dv, v0, shared_desc,
+                            minmax_out, minmax_out ? vols_per_sample : 1);
+            } else {
+                auto kern = quad ? k_bl_inv_h4<NF, CPT> : k_bl_inv_h<NF, CPT>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_hi, stream,
+                            (const cf*)Y, out + (size_t)v0 * p->vol_real, g, n_cblocks, dv, v0, shared_desc,
+                            minmax_out, minmax_out ? vols_per_sample : 1);
+            }
         }
     }
     MVTB_CUDA(cudaGetLastError());
@@ -774,6 +782,7 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_inv_h<NF, CPT>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }
 #endif

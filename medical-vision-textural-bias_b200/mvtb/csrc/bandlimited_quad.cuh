@@ -296,3 +296,176 @@ k_bl_inv_h4(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_c
     }
 }
 
+// ------------------------------------------------------------------ inverse, quads, two ADJACENT columns per thread
+// Same arithmetic as k_bl_inv_h4 for W*D even: the two columns of a thread are neighbours, so the rows of Y
+// arrive as one 16-byte load and every output row leaves as one 8-byte store (half the address arithmetic and
+// store instructions).  Index math is 32-bit (a volume has < 2^31 voxels; |f| n < 2^31).
+__device__ __forceinline__ void bl_unit32(int f, int n, int N, float* c, float* s) {
+    int m = (f * n) % N;
+    if (m < 0) m += N;
+    sincospif(2.0f * (float)m / (float)N, s, c);
+}
+
+#ifdef MVTB_EMU
+__device__ __forceinline__ void st_stream2(float* p, float a, float b) { p[0] = a; p[1] = b; }
+#else
+__device__ __forceinline__ void st_stream2(float* p, float a, float b) { __stcs((float2*)p, make_float2(a, b)); }
+#endif
+
+template <int NF>
+__global__ void __launch_bounds__(256, 2)
+k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
+             const BlVol* __restrict__ vols, int vol_base, int shared_desc,
+             float* __restrict__ minmax, int vols_per_sample) {
+    constexpr int NT = BlDims<NF>::NT;
+    MVTB_DYN_SMEM(smem_raw);
+    const int H = g.H, H2 = H / 2, H4 = H / 4;
+    const int NC = (int)g.NC;
+    float* sc = (float*)smem_raw;
+    cf* seh = (cf*)(sc + (H2 + 1) * NT);
+    const int tid = threadIdx.x;
+    const int vol = blockIdx.x / n_cblocks;
+    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
+    const int npw = bv.npw;
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
+    for (int e = tid; e < MVTB_BL_MAX_PW * (H2 + 1); e += blockDim.x) {
+        const int s = e / (H2 + 1), h = e - s * (H2 + 1);
+        float c_ = 0.f, s_ = 0.f;
+        if (s < npw) bl_unit32(bv.pw[s].fh, h, H, &c_, &s_);
+        seh[e] = cmk(c_, s_);
+    }
+    __syncthreads();
+    bool podd[MVTB_BL_MAX_PW];
+    MVTB_UNROLL
+    for (int s = 0; s < MVTB_BL_MAX_PW; ++s) podd[s] = s < npw && (bv.pw[s].fh & 1);
+
+    int col = ((blockIdx.x - vol * n_cblocks) * blockDim.x + tid) * 2;
+    const bool ok = col < NC;
+    if (!ok) col = NC - 2;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
+    float2 y2[2][NF];
+    float2 E[2][MVTB_BL_MAX_PW];
+    {
+        const cf* yv = Y + (size_t)vol * NF * NC + col;
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) {
+            const float4 y = *reinterpret_cast<const float4*>(yv + (size_t)f * NC);
+            const float cfw = f == 0 ? 1.f : 2.f;
+            y2[0][f] = make_float2(cfw * y.x, cfw * y.y);
+            y2[1][f] = make_float2(cfw * y.z, cfw * y.w);
+        }
+        MVTB_UNROLL
+        for (int k = 0; k < 2; ++k) {
+            const int w = (col + k) / g.D, d = (col + k) - w * g.D;
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                E[k][s] = make_float2(0.f, 0.f);
+                if (s < npw) {
+                    float cw, sw, cd, sd;
+                    bl_unit32(bv.pw[s].fw, w, g.W, &cw, &sw);
+                    bl_unit32(bv.pw[s].fd, d, g.D, &cd, &sd);
+                    const float amp = bv.pw[s].amp;
+                    E[k][s] = make_float2(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
+                }
+            }
+        }
+    }
+    float* ov = out + (size_t)vol * H * NC + col;
+    {
+        float2 cs[NF];
+        bl_row<NF>(sc + H4 * NT, cs);
+        float v0[2], vn[2], vq[2], v3q[2];
+        MVTB_UNROLL
+        for (int k = 0; k < 2; ++k) {
+            v0[k] = 0.f; vn[k] = 0.f;
+            float2 pq = make_float2(0.f, 0.f);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                v0[k] += y2[k][f].x;
+                vn[k] += (f & 1) ? -y2[k][f].x : y2[k][f].x;
+                pq = fma2(y2[k][f], cs[f], pq);
+            }
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                const cf e2 = seh[s * (H2 + 1) + H2], e4 = seh[s * (H2 + 1) + H4];
+                v0[k] += E[k][s].x;
+                vn[k] += E[k][s].x * e2.x - E[k][s].y * e2.y;
+                pq = fma2(E[k][s], e4, pq);
+            }
+            vq[k] = pq.x - pq.y; v3q[k] = pq.x + pq.y;
+            lo = fminf(fminf(lo, v0[k]), fminf(vn[k], fminf(vq[k], v3q[k])));
+            hi = fmaxf(fmaxf(hi, v0[k]), fmaxf(vn[k], fmaxf(vq[k], v3q[k])));
+        }
+        if (ok) {
+            st_stream2(ov, v0[0], v0[1]);
+            st_stream2(ov + (size_t)H2 * NC, vn[0], vn[1]);
+            st_stream2(ov + (size_t)H4 * NC, vq[0], vq[1]);
+            st_stream2(ov + (size_t)(H - H4) * NC, v3q[0], v3q[1]);
+        }
+    }
+    float* pa = ov + NC;
+    float* pb = ov + (size_t)(H - 1) * NC;
+    float* pc = ov + (size_t)(H2 - 1) * NC;
+    float* pd = ov + (size_t)(H2 + 1) * NC;
+    const int nq = H4 - 1;
+    for (int h = 1; h <= nq; ++h) {
+        float2 cs[NF];
+        bl_row<NF>(sc + h * NT, cs);
+        float2 eh[MVTB_BL_MAX_PW];
+        MVTB_UNROLL
+        for (int s = 0; s < MVTB_BL_MAX_PW; ++s) eh[s] = seh[s * (H2 + 1) + h];
+        float v1[2], v2[2], v3[2], v4[2];
+        MVTB_UNROLL
+        for (int k = 0; k < 2; ++k) {
+            float2 pe = make_float2(0.f, 0.f), po = make_float2(0.f, 0.f);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                if (f & 1) po = fma2(y2[k][f], cs[f], po);
+                else pe = fma2(y2[k][f], cs[f], pe);
+            }
+            MVTB_UNROLL
+            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+                if (podd[s]) po = fma2(E[k][s], eh[s], po);
+                else pe = fma2(E[k][s], eh[s], pe);
+            }
+            const float2 sm = add2(pe, po);
+            const float2 df = add2(pe, make_float2(-po.x, -po.y));
+            v1[k] = sm.x - sm.y; v2[k] = sm.x + sm.y; v3[k] = df.x + df.y; v4[k] = df.x - df.y;
+            lo = fminf(fminf(lo, fminf(v1[k], v2[k])), fminf(v3[k], v4[k]));
+            hi = fmaxf(fmaxf(hi, fmaxf(v1[k], v2[k])), fmaxf(v3[k], v4[k]));
+        }
+        if (ok) {
+            st_stream2(pa, v1[0], v1[1]);
+            st_stream2(pb, v2[0], v2[1]);
+            st_stream2(pc, v3[0], v3[1]);
+            st_stream2(pd, v4[0], v4[1]);
+        }
+        pa += NC; pd += NC;
+        pb -= NC; pc -= NC;
+    }
+    if (minmax != nullptr) {
+        __shared__ float s_lo[32], s_hi[32];
+        MVTB_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        const int lane = tid & 31, wp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+        if (lane == 0) { s_lo[wp] = lo; s_hi[wp] = hi; }
+        __syncthreads();
+        if (wp == 0) {
+            lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+            hi = lane < nw ? s_hi[lane] : __int_as_float((int)0xff800000u);
+            MVTB_UNROLL
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+            }
+            if (lane == 0) {
+                float* mm = minmax + 2 * ((vol_base + vol) / vols_per_sample);
+                bl_atomic_min(mm, lo);
+                bl_atomic_max(mm + 1, hi);
+            }
+        }
+    }
+}

@@ -140,11 +140,28 @@ def minmax(x: torch.Tensor, n_samples: int = 1) -> torch.Tensor:
 
 
 def salt_pepper(x: torch.Tensor, p: float, *, u: Optional[torch.Tensor] = None, seed: int = 0, offset: int = 0,
-                n_samples: int = 1, mm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Salt-and-pepper select (F:465-482) per sample; u injected (bit-exact parity) or Philox(seed, offset)."""
+                n_samples: int = 1, mm: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                sparse: bool = False) -> torch.Tensor:
+    """Salt-and-pepper select (F:465-482) per sample; u injected (bit-exact parity) or Philox(seed, offset).
+
+    sparse=True (Philox only): the geometric-gap Bernoulli sampler of mvtb_salt_pepper_sparse_f32, cost ~ p;
+    `offset` then counts blocks of 256 voxels (advance it by n_samples * ceil(n_per_sample / 256) per call)."""
     L = _lib.lib()
     if mm is None:
         mm = minmax(x, n_samples)
+    if sparse:
+        if u is not None:
+            raise ValueError("sparse=True draws its own random field; it cannot take injected uniforms")
+        y = x if out is None or out.data_ptr() == x.data_ptr() else out.copy_(x)
+        if out is None:
+            y = x.clone()
+        table = torch.empty(_lib.SP_BLOCK, dtype=torch.int32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = L.mvtb_salt_pepper_sparse_f32(_ptr(y), y.numel() // max(n_samples, 1), n_samples,
+                                               C.c_uint64(seed & (2 ** 64 - 1)), C.c_uint64(offset & (2 ** 64 - 1)),
+                                               C.c_float(p), _ptr(mm), _ptr(table), _stream(x.device))
+        _lib.check(L, rc)
+        return y
     if u is not None and (u.shape != x.shape or u.dtype != torch.float32 or u.device != x.device or not u.is_contiguous()):
         raise ValueError("u must be a contiguous float32 tensor of x's shape on x's device")
     y = torch.empty_like(x) if out is None else out
@@ -180,7 +197,7 @@ def wrap_fold(x: torch.Tensor, alpha: float) -> torch.Tensor:
 # ----------------------------------------------------------------------------- batched chain-127 convenience
 def chain127(x: torch.Tensor, *, r: float, spike_idx: Optional[Sequence[Sequence[int]]], intensity: float,
              alpha: Optional[float], p: Optional[float], u: Optional[torch.Tensor] = None, seed: int = 0,
-             offset: int = 0) -> torch.Tensor:
+             offset: int = 0, sparse: bool = False) -> torch.Tensor:
     """disk -> plane-wave spike -> wrap -> S&P on a batch (B, C, H, W, D), each (C,H,W,D) sample treated
     exactly as one pass through the 127-series Compose (one spike location per sample, shared by its
     channels; S&P min/max over the whole sample).  spike_idx: per-sample fftshift-ed (h,w,d), or None."""
@@ -195,4 +212,4 @@ def chain127(x: torch.Tensor, *, r: float, spike_idx: Optional[Sequence[Sequence
     if p is None:
         return kspace_chain(x, 3, descs)
     y, mm = kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C_)
-    return salt_pepper(y, p, u=u, seed=seed, offset=offset, n_samples=B_, mm=mm, out=y)
+    return salt_pepper(y, p, u=u, seed=seed, offset=offset, n_samples=B_, mm=mm, out=y, sparse=sparse)

@@ -51,3 +51,49 @@ def uniform_f32(n, seed, offset):
     key[:, 1] = np.uint32((seed >> 32) & 0xFFFFFFFF)
     r = philox4x32_10(ctr, key).reshape(-1)[:n]
     return ((r >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- sparse Bernoulli sampler
+SP_BLOCK = 256
+
+
+def sparse_table(p):
+    """T[k] = floor(2^32 (1 - (1-p)^(k+1))) with the power by repeated float64 multiplication
+    (restates mvtb_sparse_table, csrc/voxel_ops.cu)."""
+    q = np.float64(1.0) - np.float64(np.float32(p))
+    t = np.float64(1.0)
+    out = np.zeros(SP_BLOCK, dtype=np.uint32)
+    for k in range(SP_BLOCK):
+        t = t * q
+        v = np.floor((np.float64(1.0) - t) * np.float64(4294967296.0))
+        out[k] = np.uint32(min(max(v, 0.0), 4294967295.0))
+    return out
+
+
+def sparse_hits(n_per_sample, n_samples, seed, offset, p):
+    """Positions (flat index into the whole buffer) and kinds (1 = salt/max, 0 = pepper/min) that
+    mvtb_salt_pepper_sparse_f32 touches.  Pure-Python loops: small cases only."""
+    T = sparse_table(p).astype(np.uint64)
+    bps = (n_per_sample + SP_BLOCK - 1) // SP_BLOCK
+    pos_out, kind_out = [], []
+    key = np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], dtype=np.uint32)
+    for s in range(n_samples):
+        for b in range(bps):
+            j0 = b * SP_BLOCK
+            length = min(SP_BLOCK, n_per_sample - j0)
+            gb = offset + s * bps + b
+            pos, call, done = -1, 0, False
+            while not done:
+                ctr = np.array([[gb & 0xFFFFFFFF, (gb >> 32) & 0xFFFFFFFF, call, 0x5350]], dtype=np.uint32)
+                r = philox4x32_10(ctr, key)[0]
+                for t in range(2):
+                    w = np.uint64(r[t])
+                    gap = int(np.searchsorted(T, w, side="right"))       # smallest k with w < T[k]
+                    pos += gap + 1
+                    if not done and pos < length:
+                        pos_out.append(s * n_per_sample + j0 + pos)
+                        kind_out.append((int(r[2]) >> t) & 1)
+                    else:
+                        done = True
+                call += 1
+    return np.array(pos_out, dtype=np.int64), np.array(kind_out, dtype=np.int64)
