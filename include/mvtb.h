@@ -138,6 +138,8 @@ int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W,
 #define MVTB_K_BL_MID 7
 #define MVTB_K_BL_INV_W 8
 #define MVTB_K_BL_INV_H 9
+#define MVTB_K_SPIKE_REDUCE 10
+#define MVTB_K_SPIKE_APPLY 11
 #define MVTB_K_KINDS 16
 int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
 /* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */

@@ -705,9 +705,14 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         cf* G = Y + (size_t)chunk * NF * g.NC;
         {
             ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
-            if (quad) {
-                // one column per thread, 16 loads in flight, 3 CTAs/SM while the accumulators allow (measured best)
-                const int ncb1 = (int)((g.NC + kColThreads - 1) / kColThreads);
+            const int ncb1 = (int)((g.NC + kColThreads - 1) / kColThreads);
+            if (quad && NF <= 16 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && p->opt_async) {
+                // cp.async staging ring: bytes in flight no longer limited by registers
+                const size_t smem_a = smem_h + sizeof(float) * kBlStages * 1024;
+                auto kern = k_bl_fwd_h4a<NF>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_a, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1);
+            } else if (quad) {
+                // one column per thread, 16 loads in flight, 3 CTAs/SM while the accumulators allow
                 auto kern = k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>;
                 MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1);
             } else {
@@ -783,6 +788,7 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }
 #endif

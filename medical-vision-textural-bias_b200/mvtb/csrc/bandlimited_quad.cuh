@@ -469,3 +469,103 @@ k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_
         }
     }
 }
+
+// ------------------------------------------------------------------ forward, quads, cp.async staging ring
+// k_bl_fwd_h4 is bound by load latency: its bytes in flight are limited by registers (16 loads x 24 warps).
+// Here the four rows of a quad for the CTA's 256 columns (4 KB) are copied global -> shared with one 16-byte
+// cp.async (LDGSTS) per thread, kBlStages quads ahead, so ~28 KB per CTA are in flight without holding
+// registers; the threads then read their own column from shared memory.  Needs W*D % 4 == 0 and a 16-byte
+// aligned input (else the register-staged kernel runs).
+static const int kBlStages = 8;
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+#ifdef MVTB_EMU
+    for (int i = 0; i < 4; ++i) smem_dst[i] = gsrc[i];
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef MVTB_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef MVTB_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256, 3)
+k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
+    constexpr int NT = BlDims<NF>::NT, S = kBlStages;
+    MVTB_DYN_SMEM(smem_raw);
+    const int H = g.H, H2 = H / 2, H4 = H / 4;
+    float* sc = (float*)smem_raw;                       // (cos, sin) rows 0 .. H/2
+    float* ring = sc + (H2 + 1) * NT;                   // [S][4][256] floats
+    const int tid = threadIdx.x;
+    const long long vol = blockIdx.x / n_cblocks;
+    const long long c0 = (long long)(blockIdx.x - vol * n_cblocks) * 256;
+    const float* xv = x + vol * H * g.NC;
+
+    // this thread's 16-byte piece of every stage: row r of the quad, columns c0 + 4 j .. + 3
+    const int r = tid >> 6, j = tid & 63;
+    const bool piece_ok = c0 + 4 * j < g.NC;
+    const float* src0;                                  // row of quad q = 1 for this thread's r
+    long long step;                                     // rows advance by +-NC per quad
+    if (r == 0)      { src0 = xv + g.NC;                          step = g.NC; }
+    else if (r == 1) { src0 = xv + (long long)(H - 1) * g.NC;     step = -g.NC; }
+    else if (r == 2) { src0 = xv + (long long)(H2 - 1) * g.NC;    step = -g.NC; }
+    else             { src0 = xv + (long long)(H2 + 1) * g.NC;    step = g.NC; }
+    src0 += c0 + 4 * j;
+    float* dst0 = ring + r * 256 + 4 * j;
+    const int nq = H4 - 1;
+    for (int q = 1; q < S; ++q) {                       // quads 1 .. S-1 in flight before the loop
+        if (q <= nq && piece_ok) cp_async16(dst0 + ((q - 1) % S) * 1024, src0 + (long long)(q - 1) * step);
+        cp_async_commit();
+    }
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
+
+    const long long col = c0 + tid;
+    const bool ok = col < g.NC;
+    const long long colc = ok ? col : g.NC - 1;
+    float2 acc[NF];
+    __syncthreads();                                    // table ready
+    {
+        float2 cs[NF];
+        bl_row<NF>(sc + H4 * NT, cs);
+        const float x0 = ld_stream(xv + colc);
+        const float xn = ld_stream(xv + (long long)H2 * g.NC + colc);
+        const float a = ld_stream(xv + (long long)H4 * g.NC + colc);
+        const float b = ld_stream(xv + (long long)(H - H4) * g.NC + colc);
+        const float2 eo = make_float2(a + b, b - a);
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) acc[f] = fma2(eo, cs[f], make_float2(x0 + ((f & 1) ? -xn : xn), 0.f));
+    }
+    for (int q = 1; q <= nq; ++q) {
+        cp_async_wait<S - 2>();                         // this thread's piece of quad q has landed
+        __syncthreads();                                // ... everyone's has, and stage(q-1) is no longer being read
+        {
+            const int qn = q - 1 + S;                   // refill the stage read in the previous iteration
+            if (qn <= nq && piece_ok) cp_async16(dst0 + ((qn - 1) % S) * 1024, src0 + (long long)(qn - 1) * step);
+            cp_async_commit();
+        }
+        const float* st = ring + ((q - 1) % S) * 1024 + tid;
+        const float a = st[0], b = st[256], c = st[512], d = st[768];
+        float2 cs[NF];
+        bl_row<NF>(sc + q * NT, cs);
+        const float s1 = a + b, s2 = c + d, d1 = a - b, d2 = c - d;
+        const float2 ev = make_float2(s1 + s2, d2 - d1);
+        const float2 od = make_float2(s1 - s2, -(d1 + d2));
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) acc[f] = fma2((f & 1) ? od : ev, cs[f], acc[f]);
+    }
+    if (ok) {
+        cf* yv = Y + vol * NF * g.NC + col;
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC] = acc[f];
+    }
+}

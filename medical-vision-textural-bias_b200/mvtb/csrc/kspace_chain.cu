@@ -26,6 +26,11 @@ bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, in
 int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
              int F, float* minmax_out, int vols_per_sample, void* stream);
 
+// spike_fast.cu
+bool spike_fast_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc);
+int spike_fast_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
+                     float* minmax_out, int vols_per_sample, void* stream);
+
 enum { AX_FWD = 0, AX_INV = 1, AX_MID = 2, AX_STATS = 3 };
 static const int kThreads = 256;
 
@@ -496,6 +501,8 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
         MVTB_LAUNCH(k_minmax_init, dim3((n_samples + 127) / 128), dim3(128), 0, stream, minmax_out, n_samples);
     }
 
+    if (spike_fast_eligible(p, desc, n_desc))
+        return spike_fast_chain(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream);
     int blF = 0;
     if (bl_eligible(p, desc, n_desc, &blF))
         return bl_chain(p, in, out, n_volumes, desc, n_desc, blF, minmax_out, vols_per_sample, stream);

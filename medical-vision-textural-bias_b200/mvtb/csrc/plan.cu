@@ -31,6 +31,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int configure_chain_kernels(const mvtb_plan* p);   // kspace_chain.cu: opt in to large dynamic shared memory
 int configure_bl_kernels(const mvtb_plan* p);      // bandlimited.cu
+int configure_spike_kernels(const mvtb_plan* p);   // spike_fast.cu
 
 // prime factors <= 31, twos paired into fours, ascending (the radix-31 stage comes last,
 // where the DIF stage has no twiddle multiplies)
@@ -121,6 +122,7 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     if (!p) return MVTB_ENOMEM;
     p->ndim = ndim_fft;
     p->opt_quad = 1;
+    p->opt_async = getenv("MVTB_NO_ASYNC") ? 0 : 1;
     p->chunk = chunk_volumes;
     p->device = device;
     p->num_sms = prop.multiProcessorCount;
@@ -240,6 +242,7 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
 
     int rc = configure_chain_kernels(p);
     if (rc == MVTB_OK) rc = configure_bl_kernels(p);
+    if (rc == MVTB_OK) rc = configure_spike_kernels(p);
     if (rc != MVTB_OK) { cudaFree(p->ws); cudaFree(dev); free(p); return rc; }
     *out = p;
     return MVTB_OK;
@@ -268,7 +271,7 @@ extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load()
 
 extern "C" const char* mvtb_kernel_name(int kind) {
     static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
-                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "", "", "", "", "", ""};
+                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "", "", "", ""};
     return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
 }
 

@@ -95,3 +95,31 @@ def test_bl_batch_per_sample_spikes_and_fused_minmax(cuda_device):
     assert rel_l2(y.cpu().numpy(), yg.cpu().numpy()) <= TOL
     ref2 = P.chain_127(x[2].cpu(), 12.5, idxs[2], 15.0, 0.5, 0.0, None)
     assert rel_l2(y[2].cpu().numpy(), ref2.numpy()) <= TOL
+
+
+def test_spike_fast_path_matches_general_and_is_taken(cuda_device):
+    """Spikes only (no mask, no wrap): two kernels (coefficient reduction + plane-wave axpy) instead of the FFT
+    pipeline; same result as the general path and the oracle, min/max fused."""
+    import ctypes as C
+    from mvtb import _lib, functional as Fn, host
+    from oracle import ref_port as P
+    shape = (2, 240, 240, 155)
+    x = P.synthetic_volume(21, shape)
+    idx = [(120 + 40, 120 - 33, 77 + 20), (120 - 9, 120 + 2, 77 - 61)]
+    descs = [host.make_desc(spikes=[(idx[c], host.exp_f32(15.0))]) for c in range(2)]
+    xd = x.to(cuda_device)
+    plan = Fn.get_plan(shape[1:], 2, cuda_device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    y, mm = Fn.kspace_chain(xd, 3, descs, want_minmax=True, vols_per_sample=2)
+    torch.cuda.synchronize()
+    ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    assert {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]} == {"k_spike_reduce", "k_spike_apply"}
+    assert float(mm[0, 0]) == float(y.min()) and float(mm[0, 1]) == float(y.max())
+    yg = chain(xd, descs, True)
+    assert rel_l2(y.cpu().numpy(), yg.cpu().numpy()) <= TOL
+    for c in range(2):
+        ref = P.plane_wave_spike(x[c:c + 1], idx[c], 15.0)
+        assert rel_l2(y[c:c + 1].cpu().numpy(), ref.numpy()) <= TOL

@@ -9,7 +9,7 @@ CS=medical-vision-textural-bias_b200/mvtb/csrc
 mkdir -p tests/cuemu/_build
 cp tests/cuemu/_build/libmvtb_emu.so /tmp/libmvtb_emu.orig.so 2>/dev/null || true
 g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -shared -fPIC -DMVTB_EMU -Itests/cuemu -x c++ \
-    $CS/plan.cu $CS/kspace_chain.cu $CS/voxel_ops.cu $CS/bandlimited.cu tests/cuemu/cuemu.cpp -o tests/cuemu/_build/libmvtb_emu.so
+    $CS/plan.cu $CS/kspace_chain.cu $CS/voxel_ops.cu $CS/bandlimited.cu $CS/spike_fast.cu tests/cuemu/cuemu.cpp -o tests/cuemu/_build/libmvtb_emu.so
 ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0:verify_asan_link_order=0 \
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) \
     python -m pytest tests/test_emu_bandlimited.py tests/test_emu_inplace_sp.py tests/test_emu_kernels.py -x -q -p no:cacheprovider
