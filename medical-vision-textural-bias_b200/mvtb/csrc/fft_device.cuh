@@ -151,6 +151,93 @@ __device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_str
     }
 }
 
+// Two consecutive stages (radices R1 then R2, both <= 5) fused in registers: the same arithmetic, tables and
+// positions as running fft_stage<R1> and fft_stage<R2> back to back, but one pass over shared memory and one
+// barrier instead of two.  A task owns the R1*R2 elements  blk*L + p1*(L/R1) + p2*(L/(R1 R2)) + j2.
+template <int R1, int R2, bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_stride, int count,
+                                           int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    constexpr int R = R1 * R2;
+    const int m1 = L / R1, m2 = m1 / R2;
+    const int per_seq = n / R;
+    const int total = per_seq * count;
+    const int ts1 = n / L, ts2 = n / m1;
+    for (int task = tid; task < total; task += nthr) {
+        int sq, b;
+        if (SEQ_FAST) { sq = task % count; b = task / count; }
+        else          { b = task % per_seq; sq = task / per_seq; }
+        const int blk = b / m2, j2 = b - blk * m2;
+        cf* p = base + (size_t)sq * seq_stride + (size_t)(blk * L + j2) * elem_stride;
+        const int e1 = m1 * elem_stride, e2 = m2 * elem_stride;
+        cf v[R1][R2];
+        MVTB_UNROLL
+        for (int a = 0; a < R1; ++a) {
+            MVTB_UNROLL
+            for (int c = 0; c < R2; ++c) v[a][c] = p[a * e1 + c * e2];
+        }
+        if (!INV) {
+            MVTB_UNROLL
+            for (int c = 0; c < R2; ++c) {                  // stage 1: over p1, twiddle w_L^(j1 q1), j1 = c*m2 + j2
+                cf t[R1];
+                MVTB_UNROLL
+                for (int a = 0; a < R1; ++a) t[a] = v[a][c];
+                Butterfly<R1, false>::run(t, tw, 0);
+                const int j1 = (c * m2 + j2) * ts1;
+                MVTB_UNROLL
+                for (int a = 1; a < R1; ++a) t[a] = cmul(t[a], __ldg(tw + j1 * a));
+                MVTB_UNROLL
+                for (int a = 0; a < R1; ++a) v[a][c] = t[a];
+            }
+            MVTB_UNROLL
+            for (int a = 0; a < R1; ++a) {                  // stage 2: over p2, twiddle w_m1^(j2 q2)
+                Butterfly<R2, false>::run(v[a], tw, 0);
+                if (j2 != 0) {
+                    MVTB_UNROLL
+                    for (int c = 1; c < R2; ++c) v[a][c] = cmul(v[a][c], __ldg(tw + j2 * c * ts2));
+                }
+            }
+        } else {
+            MVTB_UNROLL
+            for (int a = 0; a < R1; ++a) {
+                if (j2 != 0) {
+                    MVTB_UNROLL
+                    for (int c = 1; c < R2; ++c) v[a][c] = cmulc(v[a][c], __ldg(tw + j2 * c * ts2));
+                }
+                Butterfly<R2, true>::run(v[a], tw, 0);
+            }
+            MVTB_UNROLL
+            for (int c = 0; c < R2; ++c) {
+                cf t[R1];
+                const int j1 = (c * m2 + j2) * ts1;
+                t[0] = v[0][c];
+                MVTB_UNROLL
+                for (int a = 1; a < R1; ++a) t[a] = cmulc(v[a][c], __ldg(tw + j1 * a));
+                Butterfly<R1, true>::run(t, tw, 0);
+                MVTB_UNROLL
+                for (int a = 0; a < R1; ++a) v[a][c] = t[a];
+            }
+        }
+        MVTB_UNROLL
+        for (int a = 0; a < R1; ++a) {
+            MVTB_UNROLL
+            for (int c = 0; c < R2; ++c) p[a * e1 + c * e2] = v[a][c];
+        }
+    }
+}
+
+template <bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage2_dispatch(int R1, int R2, cf* base, int seq_stride, int elem_stride, int count,
+                                                    int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    const int code = R1 * 8 + R2;
+    switch (code) {
+#define MVTB_CASE2(A, B) case A * 8 + B: fft_stage2<A, B, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
+        MVTB_CASE2(2, 3) MVTB_CASE2(2, 4) MVTB_CASE2(2, 5) MVTB_CASE2(3, 3) MVTB_CASE2(3, 4) MVTB_CASE2(3, 5)
+        MVTB_CASE2(4, 4) MVTB_CASE2(4, 5)
+#undef MVTB_CASE2
+        default: break;
+    }
+}
+
 // MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all).  The radix-31
 // butterfly alone needs > 128 registers, so kernels for axes without big primes are instantiated without it.
 template <bool INV, bool SEQ_FAST, int MAXR>
@@ -178,15 +265,23 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stri
     }
 }
 
-// Whole transform; the caller has synchronised before, and a __syncthreads() follows every stage.
+// Whole transform; the caller has synchronised before, and a __syncthreads() follows every (fused) stage.
+// ax.fuse[s] = 1 marks stage s as fused with stage s+1 (set at plan creation, never overlapping).
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr) {
     int L = ax.n;
     for (int s = 0; s < ax.nstage; ++s) {
         const int R = ax.radix[s];
-        fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
-        L /= R;
+        if (ax.fuse[s]) {
+            const int R2 = ax.radix[s + 1];
+            fft_stage2_dispatch<false, SEQ_FAST>(R, R2, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+            L /= R * R2;
+            ++s;
+        } else {
+            fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+            L /= R;
+        }
         __syncthreads();
     }
 }
@@ -194,11 +289,18 @@ __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr) {
-    int L = 1;
+    int L = 1;                                   // block length of the stages already undone
     for (int s = ax.nstage - 1; s >= 0; --s) {
         const int R = ax.radix[s];
-        L *= R;
-        fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        if (s > 0 && ax.fuse[s - 1]) {
+            const int R1 = ax.radix[s - 1];
+            L *= R * R1;
+            fft_stage2_dispatch<true, SEQ_FAST>(R1, R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+            --s;
+        } else {
+            L *= R;
+            fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+        }
         __syncthreads();
     }
 }

@@ -17,6 +17,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "fft_device.cuh"
 
 namespace mvtb {
@@ -86,7 +88,7 @@ __device__ __forceinline__ void block_minmax_commit(float lo, float hi, float* m
 }
 
 // ------------------------------------------------------------------ axis 0: real rows <-> half spectrum
-#define MVTB_MINB(MAXR) ((MAXR) <= 5 ? 3 : ((MAXR) <= 13 ? 2 : 1))
+#define MVTB_MINB(MAXR) ((MAXR) <= 13 ? 2 : 1)
 
 template <int MAXR>
 __global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
@@ -475,6 +477,22 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
     if (minmax_out && vols_per_sample < 1) { set_error("chain: vols_per_sample=%d", vols_per_sample); return MVTB_EINVAL; }
     if (n_volumes == 0) return MVTB_OK;
     MVTB_CUDA(cudaSetDevice(p->device));
+
+    std::vector<mvtb_chain_desc> shifted;
+    if (p->lead_drop > 0) {                                // the plan dropped leading length-1 axes: shift the descriptors
+        shifted.assign(desc, desc + n_desc);
+        for (int i = 0; i < n_desc; ++i) {
+            mvtb_chain_desc& d = shifted[i];
+            if (d.mask_ndim > p->ndim) d.mask_ndim = p->ndim;
+            if (d.wrap_naxes > p->ndim) d.wrap_naxes = p->ndim;
+            for (int s = 0; s < d.n_spikes && s < MVTB_MAX_SPIKES; ++s) {
+                for (int a = 0; a < p->lead_drop; ++a)
+                    if (d.spikes[s].idx[a] != 0) { set_error("chain: spike %d index %d out of bounds for an axis of length 1", s, d.spikes[s].idx[a]); return MVTB_EINVAL; }
+                for (int a = 0; a < p->ndim; ++a) d.spikes[s].idx[a] = d.spikes[s].idx[a + p->lead_drop];
+            }
+        }
+        desc = shifted.data();
+    }
 
     const ChainGeom g = make_geom(p);
     DescPack pack;

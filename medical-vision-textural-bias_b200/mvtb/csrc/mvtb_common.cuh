@@ -55,6 +55,7 @@ struct AxisDev {
     int n;                       // axis length
     int nstage;                  // radix stages
     int radix[MVTB_MAX_STAGES];  // forward (DIF) order
+    int fuse[MVTB_MAX_STAGES];   // 1: stage s and s+1 run as one register-fused pass (fft_stage2)
     const cf* tw;                // tw[t] = exp(-2 pi i t / n), t in [0, n)
     const int* pos2k;            // position after the in-place DIF  ->  frequency bin
     const int* k2pos;            // inverse map
@@ -87,7 +88,8 @@ struct DescPack {
 #define MVTB_BL_FT 36                     // table columns: frequencies 0..35
 #define MVTB_BL_MAX_PW 2                  // out-of-box spikes per volume the inverse kernel adds as plane waves
 struct mvtb_plan {
-    int ndim;                             // FFT rank (2..4)
+    int ndim;                             // FFT rank (2..4) after dropping leading length-1 axes
+    int lead_drop;                        // how many leading length-1 FFT axes the caller's shape had
     int shape[MVTB_MAX_FFT_DIMS];         // axis 0 = LAST (contiguous) axis ... axis ndim-1 = outermost
     int nh;                               // shape[0]/2 + 1
     int chunk;                            // volumes in flight

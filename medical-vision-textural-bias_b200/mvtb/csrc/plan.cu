@@ -120,6 +120,14 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
 
     mvtb_plan* p = (mvtb_plan*)calloc(1, sizeof(mvtb_plan));
     if (!p) return MVTB_ENOMEM;
+    // Leading FFT axes of length 1 (the channel axis of a (B,1,H,W,D) batch under GibbsNoiseLayer's "rank - 1"
+    // rule, S:81) are length-1 DFTs: identity, zero mask term, even fftshift-ed index.  Drop them so that such
+    // a 4-D transform runs as the 3-D one it is; the chain entry shifts the descriptors accordingly.
+    int lead = 0;
+    while (ndim_fft - lead > 2 && fft_shape[lead] == 1) ++lead;
+    p->lead_drop = lead;
+    fft_shape += lead;
+    ndim_fft -= lead;
     p->ndim = ndim_fft;
     p->opt_quad = 1;
     p->opt_async = getenv("MVTB_NO_ASYNC") ? 0 : 1;
@@ -156,6 +164,13 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
         ax.n = n;
         ax.nstage = (int)radices[a].size();
         for (int s = 0; s < ax.nstage; ++s) ax.radix[s] = radices[a][s];
+        // greedy pairing of consecutive small radices (product <= 20) into register-fused passes
+        for (int s = 0; s < MVTB_MAX_STAGES; ++s) ax.fuse[s] = 0;
+        if (!getenv("MVTB_NO_FUSE"))
+            for (int s = 0; s + 1 < ax.nstage; ++s) {
+                const int r1 = ax.radix[s], r2 = ax.radix[s + 1];
+                if (r1 <= 5 && r2 <= 5 && r1 * r2 <= 20 && r1 * r2 != 4) { ax.fuse[s] = 1; ++s; }
+            }
         cf* tw = (cf*)(host.data() + off);
         ax.tw = (const cf*)((unsigned char*)dev + off);
         for (int t = 0; t < n; ++t) {
@@ -203,7 +218,8 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
         return MVTB_EUNSUPPORTED;
     }
     p->rows_pairs_per_cta = rp;
-    p->axis_tile = 16;
+    p->axis_tile = getenv("MVTB_AXIS_TILE") ? atoi(getenv("MVTB_AXIS_TILE")) : 16;
+    if (p->axis_tile != 4 && p->axis_tile != 8 && p->axis_tile != 16 && p->axis_tile != 32) p->axis_tile = 16;
     for (int a = 1; a < ndim_fft; ++a) {
         while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) p->axis_tile /= 2;
         if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) {
