@@ -238,10 +238,48 @@ __device__ __forceinline__ void fft_stage2_dispatch(int R1, int R2, cf* base, in
     }
 }
 
+// Any other prime radix (> 31): out-of-place direct DFT through a scratch copy of the tile, one task per output
+// element, O(R) each.  Slow but it makes every axis length work (181 = MNI, 37, 41, ...).
+template <bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage_generic(int R, cf* base, cf* scratch, int seq_stride, int elem_stride, int count,
+                                                  int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    const int m = L / R;
+    const int total = n * count;
+    const int tstep = n / L, rstep = n / R;
+    for (int task = tid; task < total; task += nthr) {
+        int sq, e;
+        if (SEQ_FAST) { sq = task % count; e = task / count; }
+        else          { e = task % n; sq = task / n; }
+        const int blk = e / L, r = e - blk * L;
+        const int q = r / m, j = r - q * m;                       // output index q of butterfly (blk, j)
+        const cf* src = base + (size_t)sq * seq_stride + (size_t)(blk * L + j) * elem_stride;
+        cf acc = cmk(0.f, 0.f);
+        int idx = 0;                                              // (p q) mod R
+        for (int p = 0; p < R; ++p) {
+            cf x = src[(size_t)p * m * elem_stride];
+            if (INV && j != 0 && p != 0) x = cmulc(x, __ldg(tw + j * p * tstep));
+            const cf w = __ldg(tw + idx * rstep);                 // w_R^(pq) = (cos, -sin)
+            acc = cadd(acc, INV ? cmulc(x, w) : cmul(x, w));
+            idx += q;
+            if (idx >= R) idx -= R;
+        }
+        if (!INV && j != 0 && q != 0) acc = cmul(acc, __ldg(tw + j * q * tstep));
+        scratch[(size_t)sq * seq_stride + (size_t)e * elem_stride] = acc;
+    }
+    __syncthreads();
+    for (int task = tid; task < total; task += nthr) {
+        int sq, e;
+        if (SEQ_FAST) { sq = task % count; e = task / count; }
+        else          { e = task % n; sq = task / n; }
+        const size_t o = (size_t)sq * seq_stride + (size_t)e * elem_stride;
+        base[o] = scratch[o];
+    }
+}
+
 // MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all).  The radix-31
 // butterfly alone needs > 128 registers, so kernels for axes without big primes are instantiated without it.
 template <bool INV, bool SEQ_FAST, int MAXR>
-__device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stride, int elem_stride, int count,
+__device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, cf* scratch, int seq_stride, int elem_stride, int count,
                                                    int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
     switch (R) {
 #define MVTB_CASE(RR) case RR: fft_stage<RR, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
@@ -254,7 +292,9 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stri
                         if (MAXR > 13) {
                             switch (R) {
                                 MVTB_CASE(17) MVTB_CASE(19) MVTB_CASE(23) MVTB_CASE(29) MVTB_CASE(31)
-                                default: break;
+                                default:
+                                    if (scratch) fft_stage_generic<INV, SEQ_FAST>(R, base, scratch, seq_stride, elem_stride, count, n, L, tw, tid, nthr);
+                                    break;
                             }
                         }
                         break;
@@ -269,7 +309,7 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, int seq_stri
 // ax.fuse[s] = 1 marks stage s as fused with stage s+1 (set at plan creation, never overlapping).
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
-                                            int tid, int nthr) {
+                                            int tid, int nthr, cf* scratch = nullptr) {
     int L = ax.n;
     for (int s = 0; s < ax.nstage; ++s) {
         const int R = ax.radix[s];
@@ -279,7 +319,7 @@ __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq
             L /= R * R2;
             ++s;
         } else {
-            fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+            fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, scratch, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
             L /= R;
         }
         __syncthreads();
@@ -288,7 +328,7 @@ __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq
 
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
-                                            int tid, int nthr) {
+                                            int tid, int nthr, cf* scratch = nullptr) {
     int L = 1;                                   // block length of the stages already undone
     for (int s = ax.nstage - 1; s >= 0; --s) {
         const int R = ax.radix[s];
@@ -299,7 +339,7 @@ __device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq
             --s;
         } else {
             L *= R;
-            fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
+            fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, scratch, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
         }
         __syncthreads();
     }

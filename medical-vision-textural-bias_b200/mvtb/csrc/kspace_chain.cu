@@ -110,7 +110,7 @@ k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh
         s[rp * pitch + j] = cmk(a, b);
     }
     __syncthreads();
-    fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr);
+    fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr);
 
     // Z = FFT(a + i b):  A[k] = (Z[k] + conj Z[n-k]) / 2,  B[k] = (Z[k] - conj Z[n-k]) / (2i)
     for (int e = tid; e < np * nh; e += nthr) {
@@ -147,7 +147,7 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
         if (k != 0 && 2 * k != n) s[rp * pitch + __ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
     }
     __syncthreads();
-    fft_inverse<false, MAXR>(ax, s, pitch, 1, np, tid, nthr);
+    fft_inverse<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr);
 
     float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
     const long long row_first = 2 * pair0;
@@ -212,7 +212,8 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     }
     __syncthreads();
 
-    if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr);
+    cf* scratch = ax.generic ? s + (size_t)n * T : nullptr;
+    if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
 
     if (MODE == AX_MID) {
         const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
@@ -321,7 +322,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
         return;
     }
 
-    if (MODE != AX_FWD) fft_inverse<true, MAXR>(ax, s, 1, T, T, tid, nthr);
+    if (MODE != AX_FWD) fft_inverse<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
 
     for (int e = tid; e < n * T; e += nthr) {
         const int j = e / T;
@@ -434,7 +435,7 @@ static int launch_rows_fwd(mvtb_plan* p, const float* in, cf* ws, long long n_ro
     const long long n_pairs = (n_rows + 1) / 2;
     const int rp = p->rows_pairs_per_cta;
     const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
-    const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
+    const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf) * (p->ax[0].generic ? 2 : 1);
     switch (axis_maxr(p, 0)) {
         case 5: { auto kern = k_rows_fwd<5>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows); break; }
         case 13: { auto kern = k_rows_fwd<13>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, in, ws, p->ax[0], p->nh, p->row_pitch, rp, n_rows); break; }
@@ -455,7 +456,7 @@ static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const C
     const long long ntiles = (inner + T - 1) / T;
     const long long blocks = ntiles * outer;
     if (blocks > 0x7fffffffLL) { set_error("chain: grid too large"); return MVTB_EUNSUPPORTED; }
-    const size_t smem = (size_t)p->shape[axis] * T * sizeof(cf);
+    const size_t smem = (size_t)p->shape[axis] * T * sizeof(cf) * (p->ax[axis].generic ? 2 : 1);
     switch (axis_maxr(p, axis)) {
         case 5: { auto kern = k_axis<MODE, 5>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
         case 13: { auto kern = k_axis<MODE, 13>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
@@ -555,7 +556,7 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
             const long long n_pairs = (n_rows + 1) / 2;
             const int rp = p->rows_pairs_per_cta;
             const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
-            const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf);
+            const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf) * (p->ax[0].generic ? 2 : 1);
             const long long rows_per_sample = rows_per_vol * (minmax_out ? vols_per_sample : 1);
             // chunks need not align with samples: the kernel works from the global row number
             ProfScope prof(p, MVTB_K_ROWS_INV, stream);

@@ -56,6 +56,7 @@ struct AxisDev {
     int nstage;                  // radix stages
     int radix[MVTB_MAX_STAGES];  // forward (DIF) order
     int fuse[MVTB_MAX_STAGES];   // 1: stage s and s+1 run as one register-fused pass (fft_stage2)
+    int generic;                 // 1: some radix is a prime > 31 (fft_stage_generic: needs a scratch tile)
     const cf* tw;                // tw[t] = exp(-2 pi i t / n), t in [0, n)
     const int* pos2k;            // position after the in-place DIF  ->  frequency bin
     const int* k2pos;            // inverse map

@@ -45,7 +45,10 @@ static bool factorise(int n, std::vector<int>& out) {
             n /= p;
         }
     }
-    if (n != 1) return false;
+    for (int q = 37; n > 1; q += 2) {                       // remaining prime factors > 31: generic direct-DFT stages
+        if ((long long)q * q > n) { odd.push_back(n); n = 1; break; }
+        while (n % q == 0) { odd.push_back(q); n /= q; }
+    }
     out.clear();
     if (twos & 1) out.push_back(2);
     for (int i = 0; i < twos / 2; ++i) out.push_back(4);
@@ -146,7 +149,7 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     size_t bytes = 0;
     for (int a = 0; a < ndim_fft; ++a) {
         if (!factorise(p->shape[a], radices[a])) {
-            set_error("plan_create: axis length %d has a prime factor > 31 (unsupported)", p->shape[a]);
+            set_error("plan_create: axis length %d needs more than %d radix stages", p->shape[a], MVTB_MAX_STAGES);
             free(p);
             return MVTB_EUNSUPPORTED;
         }
@@ -163,7 +166,8 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
         AxisDev& ax = p->ax[a];
         ax.n = n;
         ax.nstage = (int)radices[a].size();
-        for (int s = 0; s < ax.nstage; ++s) ax.radix[s] = radices[a][s];
+        ax.generic = 0;
+        for (int s = 0; s < ax.nstage; ++s) { ax.radix[s] = radices[a][s]; if (ax.radix[s] > 31) ax.generic = 1; }
         // greedy pairing of consecutive small radices (product <= 20) into register-fused passes
         for (int s = 0; s < MVTB_MAX_STAGES; ++s) ax.fuse[s] = 0;
         if (!getenv("MVTB_NO_FUSE"))
@@ -208,7 +212,8 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     if ((pitch & 1) == 0) ++pitch;
     p->row_pitch = pitch;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
-    size_t per_pair = (size_t)pitch * sizeof(cf);
+    const size_t gen0 = p->ax[0].generic ? 2 : 1;              // generic stages need a scratch copy of the tile
+    size_t per_pair = (size_t)pitch * sizeof(cf) * gen0;
     int rp = (int)((size_t)64 * 1024 / per_pair);
     if (rp > 64) rp = 64;
     if (rp < 1) rp = 1;
@@ -221,8 +226,9 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->axis_tile = getenv("MVTB_AXIS_TILE") ? atoi(getenv("MVTB_AXIS_TILE")) : 16;
     if (p->axis_tile != 4 && p->axis_tile != 8 && p->axis_tile != 16 && p->axis_tile != 32) p->axis_tile = 16;
     for (int a = 1; a < ndim_fft; ++a) {
-        while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) p->axis_tile /= 2;
-        if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) > smem_cap) {
+        const size_t gen = p->ax[a].generic ? 2 : 1;
+        while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen > smem_cap) p->axis_tile /= 2;
+        if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen > smem_cap) {
             set_error("plan_create: axis of length %d does not fit in shared memory", p->shape[a]);
             cudaFree(dev); free(p);
             return MVTB_EUNSUPPORTED;

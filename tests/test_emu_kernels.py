@@ -133,6 +133,18 @@ def test_emu_chain127(name):
         assert np.allclose(mm, [z["y3"].min(), z["y3"].max()], rtol=1e-4)
 
 
+@pytest.mark.parametrize("shape", [(1, 8, 6, 37), (2, 41, 4, 6), (1, 6, 74, 5), (1, 43, 37, 47), (2, 82, 9)])
+def test_emu_prime_factors_above_31(shape):
+    """Axis lengths with prime factors > 31 run through the generic direct-DFT stage (any length works)."""
+    x = P.synthetic_volume(9, shape).numpy() + 0.1
+    nd = len(shape) - 1
+    d = host.make_desc(mask_kind=B.MASK_CENTRED, mask_ndim=nd, mask_thresh=host.gibbs_threshold(0.4, shape[1:]))
+    y, _ = emu.chain(x, nd, [d])
+    assert rel_l2(y, P.gibbs_noise(torch.from_numpy(x), 0.4).numpy()) <= TOL
+    y, _ = emu.chain(x, nd, [host.make_desc()])                  # plain round trip
+    assert rel_l2(y, x) <= TOL
+
+
 def test_emu_chunking_and_per_volume_descs():
     """n_volumes > chunk, distinct desc per volume, odd row count (zero-padded pair), min/max per sample."""
     x = P.synthetic_volume(21, (5, 3, 5, 6)).numpy()          # 5 volumes of 3x5x6: 15 rows each
@@ -202,7 +214,7 @@ def test_emu_wrap_fold_rejects_odd_axis():
 def test_emu_argument_errors():
     L = emu.lib()
     h = C.c_void_p()
-    shp = (C.c_int * 3)(8, 8, 37 * 2)      # 37 is a prime factor > 31
+    shp = (C.c_int * 3)(8, 8, 40009)       # a prime axis whose tile (plus scratch) cannot fit in shared memory
     assert L.mvtb_plan_create(C.byref(h), 3, shp, 1, 0) == B.MVTB_EUNSUPPORTED
     assert L.mvtb_plan_create(C.byref(h), 5, shp, 1, 0) == B.MVTB_EINVAL
     plan = emu.Plan((4, 6, 8))

@@ -57,3 +57,15 @@ def test_cfg5_chain_then_gibbs_layer_batch(cuda_device):
         with torch.no_grad():
             ref = P.gibbs_layer(yb[None], 0.7)[0]
         assert rel_l2(z[b].cpu().numpy(), ref.numpy()) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 181, 217, 181), (2, 74, 82, 37)])
+def test_arbitrary_axis_lengths_prime_factors_above_31(cuda_device, shape):
+    """MNI-space 181x217x181 (181 is prime) and other lengths outside 2^a 3^b 5^c ... 31^k: generic direct-DFT stages."""
+    import filters_and_operators as F
+    from oracle import ref_port as P
+    x = P.synthetic_volume(60, shape)
+    y = F.GibbsNoise(0.4)(x.to(cuda_device)).cpu()
+    assert rel_l2(y.numpy(), P.gibbs_noise(x, 0.4).numpy()) <= TOL
+    yd = F.RandFourierDiskMaskd("image", r=12.5, prob=1.)({"image": x.to(cuda_device)})["image"].cpu()
+    assert rel_l2(yd.numpy(), P.fourier_disk_mask(x, 12.5, False).numpy()) <= TOL
