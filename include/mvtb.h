@@ -153,6 +153,7 @@ unsigned long long mvtb_launch_count(void);           /* kernels launched by thi
 #define MVTB_PATH_AUTO 0
 #define MVTB_PATH_GENERAL 1
 #define MVTB_PATH_BL_PAIRS 2   /* automatic, but the band-limited H kernels use pair folding even when H % 4 == 0 */
+#define MVTB_PATH_BL_SPLIT 3   /* automatic, but the band-limited W axis, D axis and pointwise stage run as three kernels */
 int mvtb_plan_set_path(mvtb_plan* plan, int path);
 
 #ifdef __cplusplus

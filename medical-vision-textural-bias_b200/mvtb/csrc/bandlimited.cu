@@ -721,19 +721,27 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                             in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
             }
         }
-        {
-            ProfScope prof(p, MVTB_K_BL_FWD_W, stream);
-            auto kern = k_bl_fwd_w<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks_f * nv)), dim3(kWThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks_f);
-        }
-        {
+        const size_t smem_mw = smem_w + sizeof(cf) * ((size_t)K * g.D + (size_t)K * K + g.D);
+        if (NF <= 16 && smem_mw <= 72 * 1024 && p->opt_fusemid) {
+            // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);
-            MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(nv * NF)), dim3(kMidThreads), smem_mid, stream, G, g, NF, dv, v0, shared_desc, dtw);
-        }
-        {
-            ProfScope prof(p, MVTB_K_BL_INV_W, stream);
-            auto kern = k_bl_inv_w<NF>;
-            MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)G, Y, g, n_tblocks);
+            auto kern = k_bl_midw<NF>;
+            MVTB_LAUNCH(kern, dim3((unsigned)(nv * NF)), dim3(160), smem_mw, stream, Y, g, dv, v0, shared_desc);
+        } else {
+            {
+                ProfScope prof(p, MVTB_K_BL_FWD_W, stream);
+                auto kern = k_bl_fwd_w<NF>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks_f * nv)), dim3(kWThreads), smem_w, stream, (const cf*)Y, G, g, n_tblocks_f);
+            }
+            {
+                ProfScope prof(p, MVTB_K_BL_MID, stream);
+                MVTB_LAUNCH(k_bl_mid, dim3((unsigned)(nv * NF)), dim3(kMidThreads), smem_mid, stream, G, g, NF, dv, v0, shared_desc, dtw);
+            }
+            {
+                ProfScope prof(p, MVTB_K_BL_INV_W, stream);
+                auto kern = k_bl_inv_w<NF>;
+                MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)G, Y, g, n_tblocks);
+            }
         }
         {
             ProfScope prof(p, MVTB_K_BL_INV_H, stream);
@@ -789,6 +797,7 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
     return MVTB_OK;
 }
 #endif

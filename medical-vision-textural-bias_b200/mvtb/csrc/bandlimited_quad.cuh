@@ -569,3 +569,158 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
         for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC] = acc[f];
     }
 }
+
+// ------------------------------------------------------------------ W axis, D axis and pointwise stage in one kernel
+// k_bl_fwd_w + k_bl_mid + k_bl_inv_w for one (volume, f_h) plane per CTA: thread d streams its column of
+// Y[f_h][.][d] once (pair folding over w, 16 loads in flight), the 2F+1 W-bins of all columns meet in shared
+// memory for the D-axis DFT and the pointwise stage, and the same thread expands its column back and overwrites
+// Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
+template <int NF>
+__global__ void __launch_bounds__(160, 3)
+k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
+    constexpr int NT = BlDims<NF>::NT, U = 8;
+    MVTB_DYN_SMEM(smem_raw);
+    const int W = g.W, D = g.D, F = g.F, K = 2 * F + 1;
+    float* sc = (float*)smem_raw;                        // (cos, sin) rows of the W axis, 0 .. W/2
+    cf* sg = (cf*)(sc + (W / 2 + 1) * NT);               // [K][D]  W-bins of every column
+    cf* sb = sg + K * D;                                 // [K][K]  bins after the pointwise stage
+    cf* st = sb + K * K;                                 // [D]     exp(-2 pi i t / D)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int vol = blockIdx.x / NF, fh = blockIdx.x - vol * NF;
+    bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);
+    for (int e = tid; e < D; e += nthr) st[e] = __ldg(g.twD + e);
+    __syncthreads();
+    cf* yplane = Y + ((size_t)vol * NF + fh) * (size_t)W * D;
+    const int npair = (W - 1) / 2;
+
+    // ---- forward along W: column d -> sg[F +- f][d]
+    for (int d = tid; d < D; d += nthr) {
+        const cf* yv = yplane + d;
+        float2 pqx[NF], pqy[NF];
+        {
+            const cf y0 = yv[0];
+            const cf yn = (W & 1) ? cmk(0.f, 0.f) : yv[(size_t)(W / 2) * D];
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                pqx[f] = make_float2((f & 1) ? y0.x - yn.x : y0.x + yn.x, 0.f);
+                pqy[f] = make_float2((f & 1) ? y0.y - yn.y : y0.y + yn.y, 0.f);
+            }
+        }
+        int w = 1;
+        for (; w + U - 1 <= npair; w += U) {
+            cf a[U], b[U];
+            MVTB_UNROLL
+            for (int u = 0; u < U; ++u) { a[u] = yv[(size_t)(w + u) * D]; b[u] = yv[(size_t)(W - w - u) * D]; }
+            MVTB_UNROLL
+            for (int u = 0; u < U; ++u) {
+                float2 cs[NF];
+                bl_row<NF>(sc + (w + u) * NT, cs);
+                const float2 ex = make_float2(a[u].x + b[u].x, a[u].x - b[u].x);
+                const float2 ey = make_float2(a[u].y + b[u].y, a[u].y - b[u].y);
+                MVTB_UNROLL
+                for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
+            }
+        }
+        for (; w <= npair; ++w) {
+            float2 cs[NF];
+            bl_row<NF>(sc + w * NT, cs);
+            const cf a = yv[(size_t)w * D], b = yv[(size_t)(W - w) * D];
+            const float2 ex = make_float2(a.x + b.x, a.x - b.x), ey = make_float2(a.y + b.y, a.y - b.y);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) { pqx[f] = fma2(ex, cs[f], pqx[f]); pqy[f] = fma2(ey, cs[f], pqy[f]); }
+        }
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) {
+            if (f <= F) {                                // X(+f) = P - iQ, X(-f) = P + iQ
+                sg[(F + f) * D + d] = cmk(pqx[f].x + pqy[f].y, pqy[f].x - pqx[f].y);
+                if (f > 0) sg[(F - f) * D + d] = cmk(pqx[f].x - pqy[f].y, pqy[f].x + pqx[f].y);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- D axis: B[jw][jd] = sum_d G[jw][d] exp(-2 pi i fd d / D), then the pointwise stage
+    {
+        const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
+        int shape[3];
+        shape[0] = g.D; shape[1] = g.W; shape[2] = g.H;
+        for (int o = tid; o < K * K; o += nthr) {
+            const int jw = o / K, jd = o - jw * K;
+            const int fd = jd - F;
+            const int step = ((fd % D) + D) % D;
+            const cf* row = sg + jw * D;
+            cf acc = cmk(0.f, 0.f);
+            int idx = 0;
+            for (int d = 0; d < D; ++d) {
+                const cf a = row[d], w_ = st[idx];
+                acc.x = fmaf(a.x, w_.x, fmaf(-a.y, w_.y, acc.x));
+                acc.y = fmaf(a.x, w_.y, fmaf(a.y, w_.x, acc.y));
+                idx += step;
+                if (idx >= D) idx -= D;
+            }
+            int ish[3];
+            ish[0] = fd + D / 2;
+            ish[1] = (jw - F) + g.W / 2;
+            ish[2] = fh + g.H / 2;
+            sb[o] = pointwise_bin(bv.d, 3, shape, ish, acc, g.scale);
+        }
+    }
+    __syncthreads();
+
+    // ---- back along D (into registers) and along W (streamed out in place)
+    for (int d = tid; d < D; d += nthr) {
+        // G'[j][d] = sum_jd B[j][jd] exp(+2 pi i fd d / D); keep S_f = G'(+f) + G'(-f), T_f = G'(+f) - G'(-f)
+        float2 stx[NF], sty[NF];
+        const int idx0 = (int)((((long long)(-F) * d) % D + D) % D);
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) {
+            stx[f] = make_float2(0.f, 0.f);
+            sty[f] = make_float2(0.f, 0.f);
+            if (f <= F) {
+                cf gp = cmk(0.f, 0.f), gm = cmk(0.f, 0.f);
+                int idx = idx0;
+                const cf* bp = sb + (F + f) * K;
+                const cf* bm = sb + (F - f) * K;
+                for (int jd = 0; jd < K; ++jd) {
+                    const cf w_ = st[idx];                 // conj(w_) = exp(+...)
+                    const cf b1 = bp[jd], b2 = bm[jd];
+                    gp.x = fmaf(b1.x, w_.x, fmaf(b1.y, w_.y, gp.x));
+                    gp.y = fmaf(b1.y, w_.x, fmaf(-b1.x, w_.y, gp.y));
+                    gm.x = fmaf(b2.x, w_.x, fmaf(b2.y, w_.y, gm.x));
+                    gm.y = fmaf(b2.y, w_.x, fmaf(-b2.x, w_.y, gm.y));
+                    idx += d;
+                    if (idx >= D) idx -= D;
+                }
+                if (f == 0) { stx[0] = make_float2(gp.x, 0.f); sty[0] = make_float2(gp.y, 0.f); }
+                else { stx[f] = make_float2(gp.x + gm.x, gp.x - gm.x); sty[f] = make_float2(gp.y + gm.y, gp.y - gm.y); }
+            }
+        }
+        cf* yv = yplane + d;
+        {
+            cf s0 = cmk(0.f, 0.f), sn = cmk(0.f, 0.f);
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                s0.x += stx[f].x; s0.y += sty[f].x;
+                sn.x += (f & 1) ? -stx[f].x : stx[f].x;
+                sn.y += (f & 1) ? -sty[f].x : sty[f].x;
+            }
+            yv[0] = s0;
+            if ((W & 1) == 0) yv[(size_t)(W / 2) * D] = sn;
+        }
+        for (int w = 1; w <= npair; ++w) {
+            float2 cs[NF];
+            bl_row<NF>(sc + w * NT, cs);
+            float2 pqx = make_float2(0.f, 0.f), pqy = make_float2(0.f, 0.f);
+            float2 pqx2 = make_float2(0.f, 0.f), pqy2 = make_float2(0.f, 0.f);
+            MVTB_UNROLL
+            for (int f = 0; f + 1 < NF; f += 2) {
+                pqx = fma2(stx[f], cs[f], pqx); pqy = fma2(sty[f], cs[f], pqy);
+                pqx2 = fma2(stx[f + 1], cs[f + 1], pqx2); pqy2 = fma2(sty[f + 1], cs[f + 1], pqy2);
+            }
+            if (NF & 1) { pqx = fma2(stx[NF - 1], cs[NF - 1], pqx); pqy = fma2(sty[NF - 1], cs[NF - 1], pqy); }
+            const float Px = pqx.x + pqx2.x, Qx = pqx.y + pqx2.y, Py = pqy.x + pqy2.x, Qy = pqy.y + pqy2.y;
+            yv[(size_t)w * D] = cmk(Px - Qy, Py + Qx);
+            yv[(size_t)(W - w) * D] = cmk(Px + Qy, Py - Qx);
+        }
+    }
+}

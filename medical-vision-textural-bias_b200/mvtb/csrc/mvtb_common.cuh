@@ -109,6 +109,7 @@ struct mvtb_plan {
     // band-limited path (bandlimited.cu): cos/sin tables per axis, [N][MVTB_BL_FT] each
     int opt_path;
     int opt_async;                        // 1: cp.async staging ring in the forward H kernel (MVTB_NO_ASYNC=1 turns it off)
+    int opt_fusemid;                      // 1: one kernel for the W axis, D axis and pointwise stage (MVTB_NO_FUSEMID=1: three)
     int opt_quad;                         // 1: use the quad-symmetry H kernels when H % 4 == 0 (tests can turn it off)
     float* bl_tab;
     size_t bl_off[3];

@@ -134,6 +134,7 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->ndim = ndim_fft;
     p->opt_quad = 1;
     p->opt_async = getenv("MVTB_NO_ASYNC") ? 0 : 1;
+    p->opt_fusemid = getenv("MVTB_NO_FUSEMID") ? 0 : 1;
     p->chunk = chunk_volumes;
     p->device = device;
     p->num_sms = prop.multiProcessorCount;
@@ -298,9 +299,10 @@ extern "C" const char* mvtb_kernel_name(int kind) {
 }
 
 extern "C" int mvtb_plan_set_path(mvtb_plan* p, int path) {
-    if (!p || (path != MVTB_PATH_AUTO && path != MVTB_PATH_GENERAL && path != MVTB_PATH_BL_PAIRS)) { set_error("plan_set_path: bad argument"); return MVTB_EINVAL; }
+    if (!p || path < MVTB_PATH_AUTO || path > MVTB_PATH_BL_SPLIT) { set_error("plan_set_path: bad argument"); return MVTB_EINVAL; }
     p->opt_path = path == MVTB_PATH_GENERAL ? MVTB_PATH_GENERAL : MVTB_PATH_AUTO;
     p->opt_quad = path == MVTB_PATH_BL_PAIRS ? 0 : 1;
+    p->opt_fusemid = (path == MVTB_PATH_BL_SPLIT || getenv("MVTB_NO_FUSEMID")) ? 0 : 1;
     return MVTB_OK;
 }
 

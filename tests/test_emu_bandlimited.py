@@ -18,6 +18,14 @@ from oracle import ref_port as P  # noqa: E402
 TOL = 1e-5
 
 
+@pytest.fixture(autouse=True, params=[True, False], ids=["fusedmid", "splitmid"])
+def fused(request, monkeypatch):
+    """Every test runs with the W/D stage as one kernel (default) and as three (MVTB_NO_FUSEMID, read at plan create)."""
+    if not request.param:
+        monkeypatch.setenv("MVTB_NO_FUSEMID", "1")
+    return request.param
+
+
 def run(x, descs, general, chunk=4, vps=None):
     L = emu.lib()
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -48,9 +56,11 @@ def test_bl_matches_oracle_and_general(shape, r):
     assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL and rel_l2(yb, yg) <= TOL
 
 
-def test_bl_is_actually_taken():
-    """5 band-limited launches (+1 min/max init), and none of the general kernels' event kinds."""
-    x = P.synthetic_volume(1, (2, 16, 12, 8)).numpy()
+def test_bl_is_actually_taken(fused):
+    """3 band-limited launches (5 with the W/D stage split by MVTB_NO_FUSEMID), none of the general kernels' kinds,
+    and both variants agree with the oracle."""
+    xt = P.synthetic_volume(1, (2, 16, 12, 8))
+    x = xt.numpy()
     L = emu.lib()
     plan = emu.Plan((16, 12, 8), 4)
     B.check(L, L.mvtb_plan_profile(plan.h, 1))
@@ -61,7 +71,12 @@ def test_bl_is_actually_taken():
     ms, cn = (C.c_double * B.K_KINDS)(), (C.c_int * B.K_KINDS)()
     B.check(L, L.mvtb_plan_profile_read(plan.h, ms, cn))
     kinds = {L.mvtb_kernel_name(k).decode(): cn[k] for k in range(B.K_KINDS) if cn[k]}
-    assert kinds == {"k_bl_fwd_h": 1, "k_bl_fwd_w": 1, "k_bl_mid": 1, "k_bl_inv_w": 1, "k_bl_inv_h": 1}
+    want = {"k_bl_fwd_h": 1, "k_bl_mid": 1, "k_bl_inv_h": 1}
+    if not fused:
+        want.update({"k_bl_fwd_w": 1, "k_bl_inv_w": 1})
+    assert kinds == want
+    ref = torch.stack([P.fourier_disk_mask(xt[c], 2.5) for c in range(2)]).numpy()
+    assert rel_l2(y, ref) <= TOL
 
 
 def test_bl_spikes_wrap_per_volume_descs_and_minmax():

@@ -11,11 +11,12 @@ TOL = 1e-5
 
 
 def chain(x, descs, general, **kw):
+    """general: False/0 automatic, True/1 general FFT path, 2 pair-folding H kernels, 3 split W/D stage (mvtb.h)."""
     from mvtb import _lib, functional as Fn
     nvol = int(np.prod(x.shape[:-3]))
     plan = Fn.get_plan(tuple(x.shape[-3:]), nvol, x.device)
     L = _lib.lib()
-    _lib.check(L, L.mvtb_plan_set_path(plan, 1 if general else 0))
+    _lib.check(L, L.mvtb_plan_set_path(plan, int(general)))
     try:
         return Fn.kspace_chain(x, 3, descs, **kw)
     finally:
@@ -39,22 +40,28 @@ def test_bl_vs_oracle_and_general(cuda_device, shape, r):
     yg = chain(x.to(cuda_device), [d], True).cpu().numpy()
     ref = P.fourier_disk_mask(x, r, False).numpy()
     assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL and rel_l2(yb, yg) <= TOL
+    for variant in (2, 3):                        # pair-folding H kernels; W/D stage as three kernels
+        yv = chain(x.to(cuda_device), [d], variant).cpu().numpy()
+        assert rel_l2(yv, ref) <= TOL
 
 
-def test_bl_kernels_are_the_ones_launched(cuda_device):
+@pytest.mark.parametrize("split", [False, True])
+def test_bl_kernels_are_the_ones_launched(cuda_device, split):
     import ctypes as C
     from mvtb import _lib, functional as Fn, host
     x = torch.randn(2, 128, 128, 64, device=cuda_device)
     plan = Fn.get_plan((128, 128, 64), 2, cuda_device)
     L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_set_path(plan, 3 if split else 0))
     _lib.check(L, L.mvtb_plan_profile(plan, 1))
     Fn.kspace_chain(x, 3, [disk(host.disk_threshold(12.5, (128, 128, 64)))])
     torch.cuda.synchronize()
+    _lib.check(L, L.mvtb_plan_set_path(plan, 0))
     ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
     _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
     _lib.check(L, L.mvtb_plan_profile(plan, 0))
     kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
-    assert kinds == {"k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h"}
+    assert kinds == {"k_bl_fwd_h", "k_bl_mid", "k_bl_inv_h"} | ({"k_bl_fwd_w", "k_bl_inv_w"} if split else set())
 
 
 def test_bl_chain127_full_size_out_of_ball_spike(cuda_device):
