@@ -360,6 +360,9 @@ def main():
     # memory, runs the chain, and copies the result back.  The batch moves in slices so that the H2D copy of
     # slice i+1, the kernels of slice i and the D2H copy of slice i-1 overlap (three streams, PCIe is duplex).
     e2e_steps = max(1, min(args.steps, 5))
+    from mvtb import hostmem
+    affinity0 = os.sched_getaffinity(0)
+    numa = hostmem.bind_to_gpu_numa_node(local_rank)           # pinned pages are first-touched on the GPU's node
     hx = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
     hx.copy_(x)
     hy = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
@@ -402,6 +405,7 @@ def main():
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     e2e_checksum = float(hy.double().sum())
+    os.sched_setaffinity(0, affinity0)
 
     # ---- max over ranks, whole-job aggregate; NCCL only gathers statistics
     stats = torch.tensor([ms, e2e_ms, float(B), checksum], dtype=torch.float64, device=dev)
@@ -428,7 +432,7 @@ def main():
                                     "note": "8 B/voxel x voxels per step / step time: the figure the 60% target refers to"},
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(voxels * 4), "d2h_bytes_per_step": int(voxels * 4),
-                    "steps": e2e_steps, "slices_per_step": n_slices, "checksum": e2e_checksum},
+                    "steps": e2e_steps, "slices_per_step": n_slices, "checksum": e2e_checksum, "numa_rank0": numa},
             "gpu_launches": launches,
             "clocks": clocks,
             "checksum": checksum,

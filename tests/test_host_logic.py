@@ -254,3 +254,13 @@ def test_label_helpers():
     d = F.SelectChanneld(["image", "label"], (3, 0))({"image": x, "label": x})
     assert torch.equal(d["image"], x[3][None]) and torch.equal(d["label"], x[0][None])
     assert np.array_equal(F.WholeTumorTCGA("label")({"label": np.array([0, 2, 4])})["label"], [[0., 1., 1.]])
+
+
+def test_hostmem_cpulist_and_no_gpu_is_graceful():
+    """NUMA placement helper for the host-buffer path: parses sysfs cpulists; without a visible device it reports, never raises."""
+    from mvtb import hostmem
+    assert hostmem._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostmem._parse_cpulist("") == set()
+    if not torch.cuda.is_available():
+        assert hostmem.gpu_numa_node(0) is None
+        assert hostmem.bind_to_gpu_numa_node(0)["bound"] is False
