@@ -13,6 +13,7 @@
 // w_L^{jq} = tw[j q (n/L)] with j q < L, so the table index never wraps.
 #pragma once
 #include "mvtb_common.cuh"
+#include "prime_tables.cuh"
 
 namespace mvtb {
 
@@ -77,59 +78,20 @@ struct Butterfly<5, INV> {
     }
 };
 
-// Odd prime P >= 7 by the symmetric direct DFT:
-//   y_q, y_{P-q} = A_q -+ i B_q,  A_q = x0 + sum_k (x_k + x_{P-k}) cos(2 pi kq/P),
-//                                 B_q = sum_k (x_k - x_{P-k}) sin(2 pi kq/P),  k = 1..(P-1)/2
-// roots come from the axis table: w_P^t = tw[t * (n/P)] = (cos, -sin).
-template <int P, bool INV>
-struct Butterfly {
-    static __device__ __forceinline__ void run(cf* v, const cf* tw, int rstep) {
-        constexpr int H = (P - 1) / 2;
-        cf sm[H], df[H];
-        cf x0 = v[0], tot = v[0];
-        MVTB_UNROLL
-        for (int k = 0; k < H; ++k) {
-            sm[k] = cadd(v[k + 1], v[P - 1 - k]);
-            df[k] = csub(v[k + 1], v[P - 1 - k]);
-            tot = cadd(tot, sm[k]);
-        }
-        v[0] = tot;
-        MVTB_UNROLL
-        for (int q = 1; q <= H; ++q) {
-            cf A = x0, B = cmk(0.f, 0.f);
-            MVTB_UNROLL
-            for (int k = 1; k <= H; ++k) {
-                cf w = __ldg(tw + ((k * q) % P) * rstep);   // (cos, -sin)
-                A.x += sm[k - 1].x * w.x;
-                A.y += sm[k - 1].y * w.x;
-                B.x -= df[k - 1].x * w.y;
-                B.y -= df[k - 1].y * w.y;
-            }
-            cf r = INV ? cmuli(B) : cmulni(B);
-            v[q] = cadd(A, r);
-            v[P - q] = csub(A, r);
-        }
-    }
-};
+// ---- exact division of small non-negative ints by a loop-invariant divisor: x / d = umulhi(x, M) when x d < 2^32
+struct FastDiv { int d; unsigned M; };
+__device__ __forceinline__ FastDiv fastdiv_make(int d) {
+    FastDiv f;
+    f.d = d;
+    f.M = d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u;     // floor(2^32 / d) + 1  (2^32 / d itself when d is a power of two)
+    return f;
+}
+__device__ __forceinline__ int fastdiv(int x, const FastDiv& f) { return f.d > 1 ? (int)__umulhi((unsigned)x, f.M) : x; }
 
-// One radix-R stage over `count` sequences living in shared memory.
-// element (seq s, index j) is at  base[s * seq_stride + j * elem_stride].
-// Tasks are (sequence, butterfly); SEQ_FAST picks which one is fastest across threads.
-template <int R, bool INV, bool SEQ_FAST>
-__device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_stride, int count,
-                                          int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
-    const int m = L / R;
-    const int per_seq = n / R;
-    const int total = per_seq * count;
-    const int tstep = n / L;
-    const int rstep = n / R;
-    for (int task = tid; task < total; task += nthr) {
-        int sq, b;
-        if (SEQ_FAST) { sq = task % count; b = task / count; }
-        else          { b = task % per_seq; sq = task / per_seq; }
-        const int blk = b / m, j = b - blk * m;
-        cf* p = base + (size_t)sq * seq_stride + (size_t)(blk * L + j) * elem_stride;
-        const int es = m * elem_stride;
+// One butterfly (radix R <= 5) with its stage twiddles, in place at p[q * es], q = 0..R-1; j = index inside the block.
+template <int R, bool INV, bool PRIME = (R >= 7)>
+struct StageTask {
+    static __device__ __forceinline__ void run(cf* p, int es, int j, int tstep, const cf* __restrict__ tw) {
         cf v[R];
         MVTB_UNROLL
         for (int q = 0; q < R; ++q) v[q] = p[q * es];
@@ -138,9 +100,9 @@ __device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_str
                 MVTB_UNROLL
                 for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * tstep));
             }
-            Butterfly<R, true>::run(v, tw, rstep);
+            Butterfly<R, true>::run(v, tw, 0);
         } else {
-            Butterfly<R, false>::run(v, tw, rstep);
+            Butterfly<R, false>::run(v, tw, 0);
             if (j != 0) {
                 MVTB_UNROLL
                 for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + j * q * tstep));
@@ -149,26 +111,92 @@ __device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_str
         MVTB_UNROLL
         for (int q = 0; q < R; ++q) p[q * es] = v[q];
     }
+};
+
+// Odd prime P >= 7 by the symmetric direct DFT, streamed:
+//   y_q, y_{P-q} = A_q -+ i B_q,  A_q = x0 + sum_k (x_k + x_{P-k}) cos(2 pi kq/P),
+//                                 B_q = sum_k (x_k - x_{P-k}) sin(2 pi kq/P),  k = 1..(P-1)/2
+// Only the P-1 accumulators live in registers: the inputs are read from shared memory pair by pair, and with
+// both loops unrolled the roots are compile-time literals (prime_tables.cuh) that end up as FFMA immediates.
+// (Holding all P inputs as well needed 255 registers for P = 31 and one CTA per SM.)
+template <int P, bool INV>
+struct StageTask<P, INV, true> {
+    static __device__ __forceinline__ void run(cf* p, int es, int j, int tstep, const cf* __restrict__ tw) {
+        constexpr int H = (P - 1) / 2;
+        const cf x0 = p[0];
+        cf tot = x0;
+        cf A[H], B[H];
+        MVTB_UNROLL
+        for (int q = 0; q < H; ++q) { A[q] = x0; B[q] = cmk(0.f, 0.f); }
+        MVTB_UNROLL
+        for (int k = 1; k <= H; ++k) {
+            cf a = p[k * es], b = p[(P - k) * es];
+            if (INV && j != 0) {
+                a = cmulc(a, __ldg(tw + j * k * tstep));
+                b = cmulc(b, __ldg(tw + j * (P - k) * tstep));
+            }
+            const cf sm = cadd(a, b), df = csub(a, b);
+            tot = cadd(tot, sm);
+            MVTB_UNROLL
+            for (int q = 1; q <= H; ++q) {
+                const float c = PrimeTab<P>::c((k * q) % P), sn = PrimeTab<P>::s((k * q) % P);
+                A[q - 1].x = fmaf(sm.x, c, A[q - 1].x);
+                A[q - 1].y = fmaf(sm.y, c, A[q - 1].y);
+                B[q - 1].x = fmaf(df.x, sn, B[q - 1].x);
+                B[q - 1].y = fmaf(df.y, sn, B[q - 1].y);
+            }
+        }
+        p[0] = tot;
+        MVTB_UNROLL
+        for (int q = 1; q <= H; ++q) {
+            const cf r = INV ? cmuli(B[q - 1]) : cmulni(B[q - 1]);
+            cf yp = cadd(A[q - 1], r), ym = csub(A[q - 1], r);
+            if (!INV && j != 0) {
+                yp = cmul(yp, __ldg(tw + j * q * tstep));
+                ym = cmul(ym, __ldg(tw + j * (P - q) * tstep));
+            }
+            p[q * es] = yp;
+            p[(P - q) * es] = ym;
+        }
+    }
+};
+
+// One radix-R stage over `count` sequences living in shared memory.
+// element (seq s, index j) is at  base[s * seq_stride + j * elem_stride].
+// Tasks are (sequence, butterfly).  SEQ_FAST: sequences are the fastest index across threads and
+// nthr % count == 0, so a thread keeps its sequence and strides over butterflies; otherwise butterflies are fastest.
+template <int R, bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_stride, int count,
+                                          int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    const int m = L / R;
+    const int per_seq = n / R;
+    const int tstep = n / L;
+    const int es = m * elem_stride;
+    const FastDiv dm = fastdiv_make(m);
+    if (SEQ_FAST) {
+        const int sq = tid % count, bstep = nthr / count;
+        cf* sbase = base + (size_t)sq * seq_stride;
+        for (int b = tid / count; b < per_seq; b += bstep) {
+            const int blk = fastdiv(b, dm), j = b - blk * m;
+            StageTask<R, INV>::run(sbase + (size_t)(blk * L + j) * elem_stride, es, j, tstep, tw);
+        }
+    } else {
+        const FastDiv dp = fastdiv_make(per_seq);
+        const int total = per_seq * count;
+        for (int task = tid; task < total; task += nthr) {
+            const int sq = fastdiv(task, dp), b = task - sq * per_seq;
+            const int blk = fastdiv(b, dm), j = b - blk * m;
+            StageTask<R, INV>::run(base + (size_t)sq * seq_stride + (size_t)(blk * L + j) * elem_stride, es, j, tstep, tw);
+        }
+    }
 }
 
 // Two consecutive stages (radices R1 then R2, both <= 5) fused in registers: the same arithmetic, tables and
 // positions as running fft_stage<R1> and fft_stage<R2> back to back, but one pass over shared memory and one
 // barrier instead of two.  A task owns the R1*R2 elements  blk*L + p1*(L/R1) + p2*(L/(R1 R2)) + j2.
-template <int R1, int R2, bool INV, bool SEQ_FAST>
-__device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_stride, int count,
-                                           int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
-    constexpr int R = R1 * R2;
-    const int m1 = L / R1, m2 = m1 / R2;
-    const int per_seq = n / R;
-    const int total = per_seq * count;
-    const int ts1 = n / L, ts2 = n / m1;
-    for (int task = tid; task < total; task += nthr) {
-        int sq, b;
-        if (SEQ_FAST) { sq = task % count; b = task / count; }
-        else          { b = task % per_seq; sq = task / per_seq; }
-        const int blk = b / m2, j2 = b - blk * m2;
-        cf* p = base + (size_t)sq * seq_stride + (size_t)(blk * L + j2) * elem_stride;
-        const int e1 = m1 * elem_stride, e2 = m2 * elem_stride;
+template <int R1, int R2, bool INV>
+__device__ __forceinline__ void fft_task2(cf* p, int e1, int e2, int m2, int j2, int ts1, int ts2, const cf* __restrict__ tw) {
+    {
         cf v[R1][R2];
         MVTB_UNROLL
         for (int a = 0; a < R1; ++a) {
@@ -225,6 +253,33 @@ __device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_st
     }
 }
 
+template <int R1, int R2, bool INV, bool SEQ_FAST>
+__device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_stride, int count,
+                                           int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+    constexpr int R = R1 * R2;
+    const int m1 = L / R1, m2 = m1 / R2;
+    const int per_seq = n / R;
+    const int ts1 = n / L, ts2 = n / m1;
+    const int e1 = m1 * elem_stride, e2 = m2 * elem_stride;
+    const FastDiv dm = fastdiv_make(m2);
+    if (SEQ_FAST) {
+        const int sq = tid % count, bstep = nthr / count;
+        cf* sbase = base + (size_t)sq * seq_stride;
+        for (int b = tid / count; b < per_seq; b += bstep) {
+            const int blk = fastdiv(b, dm), j2 = b - blk * m2;
+            fft_task2<R1, R2, INV>(sbase + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ts1, ts2, tw);
+        }
+    } else {
+        const FastDiv dp = fastdiv_make(per_seq);
+        const int total = per_seq * count;
+        for (int task = tid; task < total; task += nthr) {
+            const int sq = fastdiv(task, dp), b = task - sq * per_seq;
+            const int blk = fastdiv(b, dm), j2 = b - blk * m2;
+            fft_task2<R1, R2, INV>(base + (size_t)sq * seq_stride + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ts1, ts2, tw);
+        }
+    }
+}
+
 template <bool INV, bool SEQ_FAST>
 __device__ __forceinline__ void fft_stage2_dispatch(int R1, int R2, cf* base, int seq_stride, int elem_stride, int count,
                                                     int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
@@ -276,8 +331,8 @@ __device__ __forceinline__ void fft_stage_generic(int R, cf* base, cf* scratch, 
     }
 }
 
-// MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all).  The radix-31
-// butterfly alone needs > 128 registers, so kernels for axes without big primes are instantiated without it.
+// MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all): each unrolled prime
+// stage is P^2 FMAs of code, so kernels for axes without big primes are instantiated without them.
 template <bool INV, bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, cf* scratch, int seq_stride, int elem_stride, int count,
                                                    int n, int L, const cf* __restrict__ tw, int tid, int nthr) {

@@ -34,7 +34,9 @@ int spike_fast_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, c
                      float* minmax_out, int vols_per_sample, void* stream);
 
 enum { AX_FWD = 0, AX_INV = 1, AX_MID = 2, AX_STATS = 3 };
-static const int kThreads = 256;
+// Small CTAs, many per SM: a CTA is load -> barrier -> stages -> store with nothing overlapping inside it, so the
+// loads in flight come from having 4-6 CTAs per SM in different phases (256 threads x 2 CTAs measured 2-3x slower).
+static const int kThreads = 128;
 
 struct ChainGeom {
     int ndim;
@@ -88,10 +90,10 @@ __device__ __forceinline__ void block_minmax_commit(float lo, float hi, float* m
 }
 
 // ------------------------------------------------------------------ axis 0: real rows <-> half spectrum
-#define MVTB_MINB(MAXR) ((MAXR) <= 13 ? 2 : 1)
+#define MVTB_MINB(MAXR) ((MAXR) <= 5 ? 6 : 4)
 
 template <int MAXR>
-__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
+__global__ void __launch_bounds__(128, MVTB_MINB(MAXR))
 k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh, int pitch,
            int pairs_per_cta, long long n_rows) {
     MVTB_DYN_SMEM(smem_raw);
@@ -102,30 +104,35 @@ k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh
     long long rem = n_pairs - pair0;
     const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
 
-    for (int e = tid; e < np * n; e += nthr) {
-        const int rp = e / n, j = e - rp * n;
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;          // one warp per row pair: no divisions, coalesced rows
+    for (int rp = wid; rp < np; rp += nw) {
         const long long ra = 2 * (pair0 + rp);
-        const float a = in[ra * n + j];
-        const float b = (ra + 1 < n_rows) ? in[(ra + 1) * n + j] : 0.f;
-        s[rp * pitch + j] = cmk(a, b);
+        const float* pa = in + ra * n;
+        const bool hasb = ra + 1 < n_rows;
+        cf* sr = s + rp * pitch;
+        for (int j = lane; j < n; j += 32) sr[j] = cmk(pa[j], hasb ? pa[n + j] : 0.f);
     }
     __syncthreads();
     fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr);
 
     // Z = FFT(a + i b):  A[k] = (Z[k] + conj Z[n-k]) / 2,  B[k] = (Z[k] - conj Z[n-k]) / (2i)
-    for (int e = tid; e < np * nh; e += nthr) {
-        const int rp = e / nh, k = e - rp * nh;
-        const int kn = k == 0 ? 0 : n - k;
-        const cf zk = s[rp * pitch + __ldg(ax.k2pos + k)];
-        const cf zn = s[rp * pitch + __ldg(ax.k2pos + kn)];
+    for (int rp = wid; rp < np; rp += nw) {
         const long long ra = 2 * (pair0 + rp);
-        ws[ra * nh + k] = cmk(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        if (ra + 1 < n_rows) ws[(ra + 1) * nh + k] = cmk(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        const bool hasb = ra + 1 < n_rows;
+        const cf* sr = s + rp * pitch;
+        cf* wa = ws + ra * nh;
+        for (int k = lane; k < nh; k += 32) {
+            const int kn = k == 0 ? 0 : n - k;
+            const cf zk = sr[__ldg(ax.k2pos + k)];
+            const cf zn = sr[__ldg(ax.k2pos + kn)];
+            wa[k] = cmk(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+            if (hasb) wa[nh + k] = cmk(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+        }
     }
 }
 
 template <int MAXR>
-__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
+__global__ void __launch_bounds__(128, MVTB_MINB(MAXR))
 k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int nh, int pitch,
            int pairs_per_cta, long long n_rows, float* __restrict__ minmax, long long rows_per_sample,
            long long row_base) {
@@ -138,13 +145,18 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
     const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
 
     // Z[k] = A[k] + i B[k];  Z[n-k] = conj A[k] + i conj B[k]
-    for (int e = tid; e < np * nh; e += nthr) {
-        const int rp = e / nh, k = e - rp * nh;
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    for (int rp = wid; rp < np; rp += nw) {
         const long long ra = 2 * (pair0 + rp);
-        const cf A = ws[ra * nh + k];
-        const cf B = (ra + 1 < n_rows) ? ws[(ra + 1) * nh + k] : cmk(0.f, 0.f);
-        s[rp * pitch + __ldg(ax.k2pos + k)] = cmk(A.x - B.y, A.y + B.x);
-        if (k != 0 && 2 * k != n) s[rp * pitch + __ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
+        const bool hasb = ra + 1 < n_rows;
+        const cf* wa = ws + ra * nh;
+        cf* sr = s + rp * pitch;
+        for (int k = lane; k < nh; k += 32) {
+            const cf A = wa[k];
+            const cf B = hasb ? wa[nh + k] : cmk(0.f, 0.f);
+            sr[__ldg(ax.k2pos + k)] = cmk(A.x - B.y, A.y + B.x);
+            if (k != 0 && 2 * k != n) sr[__ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
+        }
     }
     __syncthreads();
     fft_inverse<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr);
@@ -155,23 +167,28 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
     if (row_last >= n_rows) row_last = n_rows - 1;
     const bool want_mm = minmax != nullptr;
     const bool uniform = want_mm && ((row_base + row_first) / rows_per_sample == (row_base + row_last) / rows_per_sample);
-    for (int e = tid; e < np * n; e += nthr) {
-        const int rp = e / n, j = e - rp * n;
+    for (int rp = wid; rp < np; rp += nw) {
         const long long ra = 2 * (pair0 + rp);
-        const cf z = s[rp * pitch + j];
-        out[ra * n + j] = z.x;
         const bool hasb = ra + 1 < n_rows;
-        if (hasb) out[(ra + 1) * n + j] = z.y;
-        if (want_mm) {
-            if (uniform) {
-                lo = fminf(lo, z.x); hi = fmaxf(hi, z.x);
-                if (hasb) { lo = fminf(lo, z.y); hi = fmaxf(hi, z.y); }
-            } else {
-                float* ma = minmax + 2 * ((row_base + ra) / rows_per_sample);
-                atomic_min_f32(ma, z.x); atomic_max_f32(ma + 1, z.x);
-                if (hasb) {
-                    float* mb = minmax + 2 * ((row_base + ra + 1) / rows_per_sample);
-                    atomic_min_f32(mb, z.y); atomic_max_f32(mb + 1, z.y);
+        const cf* sr = s + rp * pitch;
+        float* pa = out + ra * n;
+        float* ma = nullptr;
+        float* mb = nullptr;
+        if (want_mm && !uniform) {
+            ma = minmax + 2 * ((row_base + ra) / rows_per_sample);
+            mb = minmax + 2 * ((row_base + ra + 1) / rows_per_sample);
+        }
+        for (int j = lane; j < n; j += 32) {
+            const cf z = sr[j];
+            pa[j] = z.x;
+            if (hasb) pa[n + j] = z.y;
+            if (want_mm) {
+                if (uniform) {
+                    lo = fminf(lo, z.x); hi = fmaxf(hi, z.x);
+                    if (hasb) { lo = fminf(lo, z.y); hi = fmaxf(hi, z.y); }
+                } else {
+                    atomic_min_f32(ma, z.x); atomic_max_f32(ma + 1, z.x);
+                    if (hasb) { atomic_min_f32(mb, z.y); atomic_max_f32(mb + 1, z.y); }
                 }
             }
         }
@@ -194,7 +211,7 @@ __device__ __forceinline__ cf spike_value(cf ko, float amp) {
 // Axes >= 1 of the half-spectrum workspace, viewed as [outer][n][inner].
 // One CTA owns a tile of T adjacent `inner` columns over the whole axis: shared memory [n][T].
 template <int MODE, int MAXR>
-__global__ void __launch_bounds__(256, MVTB_MINB(MAXR))
+__global__ void __launch_bounds__(128, MVTB_MINB(MAXR))
 k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int ntiles,
        ChainGeom g, DescPack pack, double* __restrict__ sums) {
     MVTB_DYN_SMEM(smem_raw);
@@ -203,12 +220,16 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     const long long o = blockIdx.x / ntiles;
     const long long i0 = (long long)(blockIdx.x - o * ntiles) * T;
     cf* base = ws + o * (long long)n * inner + i0;
-    const int t = tid % T;                 // nthr % T == 0: a thread always sees the same column
+    int lgT = 0;                           // T is a power of two and nthr % T == 0: a thread always sees the same column
+    while ((1 << lgT) < T) ++lgT;
+    const int t = tid & (T - 1);
     const bool col_ok = i0 + t < inner;
+    const long long gstep = (long long)(nthr >> lgT) * inner;
 
-    for (int e = tid; e < n * T; e += nthr) {
-        const int j = e / T;
-        s[e] = col_ok ? base[(long long)j * inner + t] : cmk(0.f, 0.f);
+    {
+        const cf* gp = base + (long long)(tid >> lgT) * inner + t;
+        MVTB_UNROLL_N(4)
+        for (int e = tid; e < n * T; e += nthr, gp += gstep) s[e] = col_ok ? *gp : cmk(0.f, 0.f);
     }
     __syncthreads();
 
@@ -253,7 +274,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
         }
         // ---- per-bin part
         if (col_ok) {
-            for (int j = tid / T; j < n; j += nthr / T) {
+            for (int j = tid >> lgT; j < n; j += nthr >> lgT) {
                 const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
                 const int imn = (2 * (n / 2) - im + n) % n;
                 float meff = 1.f;
@@ -304,7 +325,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             const int k0 = (int)((i0 + t) % g.nh);
             const bool self = k0 == 0 || (2 * k0 == g.shape[0]);
             const double wt = self ? 1.0 : 2.0;
-            for (int j = tid / T; j < n; j += nthr / T) {
+            for (int j = tid >> lgT; j < n; j += nthr >> lgT) {
                 const cf K = s[j * T + t];
                 acc += wt * (double)logf(hypotf(K.x, K.y) + 1e-10f);
             }
@@ -324,9 +345,10 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
 
     if (MODE != AX_FWD) fft_inverse<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
 
-    for (int e = tid; e < n * T; e += nthr) {
-        const int j = e / T;
-        if (col_ok) base[(long long)j * inner + t] = s[e];
+    if (col_ok) {
+        cf* gp = base + (long long)(tid >> lgT) * inner + t;
+        MVTB_UNROLL_N(4)
+        for (int e = tid; e < n * T; e += nthr, gp += gstep) *gp = s[e];
     }
 }
 

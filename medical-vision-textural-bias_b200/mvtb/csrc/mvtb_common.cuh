@@ -13,12 +13,15 @@
     do { mvtb::count_launch(); cuemu::launch((grid), (block), (smem), [&]() { kern(__VA_ARGS__); }); } while (0)
 #define MVTB_DYN_SMEM(name) unsigned char* name = cuemu::g_dyn_smem
 #define MVTB_UNROLL
+#define MVTB_UNROLL_N(n)
 #else
 #include <cuda_runtime.h>
 #define MVTB_LAUNCH(kern, grid, block, smem, stream, ...) \
     do { mvtb::count_launch(); kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); } while (0)
 #define MVTB_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #define MVTB_UNROLL _Pragma("unroll")
+#define MVTB_STR_(x) #x
+#define MVTB_UNROLL_N(n) _Pragma(MVTB_STR_(unroll n))
 #endif
 
 #include "../../../include/mvtb.h"

@@ -215,9 +215,30 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
     const size_t gen0 = p->ax[0].generic ? 2 : 1;              // generic stages need a scratch copy of the tile
     size_t per_pair = (size_t)pitch * sizeof(cf) * gen0;
-    int rp = (int)((size_t)64 * 1024 / per_pair);
-    if (rp > 64) rp = 64;
-    if (rp < 1) rp = 1;
+    // Row pairs per CTA (kernels run 128 threads): at most ~32 KB of tile so that several CTAs share an SM, and
+    // among those sizes the one that wastes the fewest thread slots in the stage passes, weighting a pass by its
+    // radix (5 x 31 = 155: the radix-31 pass has 5 butterflies per pair, so 25 pairs fill 125 of 128 threads
+    // where 26 would need a second, almost empty round).
+    int rp_cap = (int)((size_t)32 * 1024 / per_pair);
+    if (rp_cap > 64) rp_cap = 64;
+    if (rp_cap < 1) rp_cap = 1;
+    int rp = rp_cap;
+    {
+        const AxisDev& ax0 = p->ax[0];
+        double best = 1e300;
+        for (int c = rp_cap; c >= (rp_cap + 1) / 2; --c) {
+            double cost = 0.0;
+            for (int s = 0; s < ax0.nstage; ++s) {
+                int R = ax0.radix[s];
+                double per_task = R > 5 ? (double)R * R : 4.0 * R;      // direct prime butterfly: R^2; small radix: ~R log R
+                if (ax0.fuse[s]) { R *= ax0.radix[s + 1]; ++s; per_task = 4.0 * R; }
+                const long long tasks = (long long)(ax0.n / R) * c;
+                cost += (double)((tasks + 127) / 128) * per_task;
+            }
+            cost /= (double)c;
+            if (cost < best - 1e-12) { best = cost; rp = c; }
+        }
+    }
     if (per_pair > smem_cap) {
         set_error("plan_create: last axis of length %d does not fit in shared memory", p->shape[0]);
         cudaFree(dev); free(p);
