@@ -478,25 +478,7 @@ k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_
 // aligned input (else the register-staged kernel runs).
 static const int kBlStages = 8;
 
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
-#ifdef MVTB_EMU
-    for (int i = 0; i < 4; ++i) smem_dst[i] = gsrc[i];
-#else
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_commit() {
-#ifndef MVTB_EMU
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-#ifndef MVTB_EMU
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-#endif
-}
+// cp_async16 / cp_async_commit / cp_async_wait: mvtb_common.cuh
 
 template <int NF>
 __global__ void __launch_bounds__(256, 3)

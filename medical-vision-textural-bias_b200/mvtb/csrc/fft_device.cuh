@@ -86,7 +86,13 @@ __device__ __forceinline__ FastDiv fastdiv_make(int d) {
     f.M = d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u;     // floor(2^32 / d) + 1  (2^32 / d itself when d is a power of two)
     return f;
 }
+__device__ __forceinline__ FastDiv fastdiv_from(int d, unsigned M) { FastDiv f; f.d = d; f.M = M; return f; }
 __device__ __forceinline__ int fastdiv(int x, const FastDiv& f) { return f.d > 1 ? (int)__umulhi((unsigned)x, f.M) : x; }
+
+// Which (sequence, butterfly) tasks a thread runs.  SEQ_FAST kernels (sequences fastest across threads,
+// nthr % count == 0) give every thread one fixed sequence `sq` and butterflies b0, b0 + bstep, ...;
+// the others enumerate task = tid, tid + nthr, ... with butterflies fastest.
+struct TaskMap { int sq, b0, bstep; };
 
 // One butterfly (radix R <= 5) with its stage twiddles, in place at p[q * es], q = 0..R-1; j = index inside the block.
 template <int R, bool INV, bool PRIME = (R >= 7)>
@@ -163,28 +169,23 @@ struct StageTask<P, INV, true> {
 
 // One radix-R stage over `count` sequences living in shared memory.
 // element (seq s, index j) is at  base[s * seq_stride + j * elem_stride].
-// Tasks are (sequence, butterfly).  SEQ_FAST: sequences are the fastest index across threads and
-// nthr % count == 0, so a thread keeps its sequence and strides over butterflies; otherwise butterflies are fastest.
 template <int R, bool INV, bool SEQ_FAST>
-__device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_stride, int count,
-                                          int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
-    const int m = L / R;
-    const int per_seq = n / R;
-    const int tstep = n / L;
+__device__ __forceinline__ void fft_stage(cf* base, int seq_stride, int elem_stride, int count, const PassDev& ps,
+                                          const cf* __restrict__ tw, const TaskMap& tm, int tid, int nthr) {
+    const int m = ps.m, L = ps.L, tstep = ps.ts1;
     const int es = m * elem_stride;
-    const FastDiv dm = fastdiv_make(m);
+    const FastDiv dm = fastdiv_from(m, ps.magic_m);
     if (SEQ_FAST) {
-        const int sq = tid % count, bstep = nthr / count;
-        cf* sbase = base + (size_t)sq * seq_stride;
-        for (int b = tid / count; b < per_seq; b += bstep) {
+        cf* sbase = base + (size_t)tm.sq * seq_stride;
+        for (int b = tm.b0; b < ps.per_seq; b += tm.bstep) {
             const int blk = fastdiv(b, dm), j = b - blk * m;
             StageTask<R, INV>::run(sbase + (size_t)(blk * L + j) * elem_stride, es, j, tstep, tw);
         }
     } else {
-        const FastDiv dp = fastdiv_make(per_seq);
-        const int total = per_seq * count;
+        const FastDiv dp = fastdiv_from(ps.per_seq, ps.magic_ps);
+        const int total = ps.per_seq * count;
         for (int task = tid; task < total; task += nthr) {
-            const int sq = fastdiv(task, dp), b = task - sq * per_seq;
+            const int sq = fastdiv(task, dp), b = task - sq * ps.per_seq;
             const int blk = fastdiv(b, dm), j = b - blk * m;
             StageTask<R, INV>::run(base + (size_t)sq * seq_stride + (size_t)(blk * L + j) * elem_stride, es, j, tstep, tw);
         }
@@ -254,38 +255,33 @@ __device__ __forceinline__ void fft_task2(cf* p, int e1, int e2, int m2, int j2,
 }
 
 template <int R1, int R2, bool INV, bool SEQ_FAST>
-__device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_stride, int count,
-                                           int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
-    constexpr int R = R1 * R2;
-    const int m1 = L / R1, m2 = m1 / R2;
-    const int per_seq = n / R;
-    const int ts1 = n / L, ts2 = n / m1;
+__device__ __forceinline__ void fft_stage2(cf* base, int seq_stride, int elem_stride, int count, const PassDev& ps,
+                                           const cf* __restrict__ tw, const TaskMap& tm, int tid, int nthr) {
+    const int m2 = ps.m, m1 = m2 * R2, L = ps.L;
     const int e1 = m1 * elem_stride, e2 = m2 * elem_stride;
-    const FastDiv dm = fastdiv_make(m2);
+    const FastDiv dm = fastdiv_from(m2, ps.magic_m);
     if (SEQ_FAST) {
-        const int sq = tid % count, bstep = nthr / count;
-        cf* sbase = base + (size_t)sq * seq_stride;
-        for (int b = tid / count; b < per_seq; b += bstep) {
+        cf* sbase = base + (size_t)tm.sq * seq_stride;
+        for (int b = tm.b0; b < ps.per_seq; b += tm.bstep) {
             const int blk = fastdiv(b, dm), j2 = b - blk * m2;
-            fft_task2<R1, R2, INV>(sbase + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ts1, ts2, tw);
+            fft_task2<R1, R2, INV>(sbase + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ps.ts1, ps.ts2, tw);
         }
     } else {
-        const FastDiv dp = fastdiv_make(per_seq);
-        const int total = per_seq * count;
+        const FastDiv dp = fastdiv_from(ps.per_seq, ps.magic_ps);
+        const int total = ps.per_seq * count;
         for (int task = tid; task < total; task += nthr) {
-            const int sq = fastdiv(task, dp), b = task - sq * per_seq;
+            const int sq = fastdiv(task, dp), b = task - sq * ps.per_seq;
             const int blk = fastdiv(b, dm), j2 = b - blk * m2;
-            fft_task2<R1, R2, INV>(base + (size_t)sq * seq_stride + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ts1, ts2, tw);
+            fft_task2<R1, R2, INV>(base + (size_t)sq * seq_stride + (size_t)(blk * L + j2) * elem_stride, e1, e2, m2, j2, ps.ts1, ps.ts2, tw);
         }
     }
 }
 
 template <bool INV, bool SEQ_FAST>
-__device__ __forceinline__ void fft_stage2_dispatch(int R1, int R2, cf* base, int seq_stride, int elem_stride, int count,
-                                                    int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
-    const int code = R1 * 8 + R2;
-    switch (code) {
-#define MVTB_CASE2(A, B) case A * 8 + B: fft_stage2<A, B, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
+__device__ __forceinline__ void fft_stage2_dispatch(cf* base, int seq_stride, int elem_stride, int count, const PassDev& ps,
+                                                    const cf* __restrict__ tw, const TaskMap& tm, int tid, int nthr) {
+    switch (ps.r1 * 8 + ps.r2) {
+#define MVTB_CASE2(A, B) case A * 8 + B: fft_stage2<A, B, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, ps, tw, tm, tid, nthr); break;
         MVTB_CASE2(2, 3) MVTB_CASE2(2, 4) MVTB_CASE2(2, 5) MVTB_CASE2(3, 3) MVTB_CASE2(3, 4) MVTB_CASE2(3, 5)
         MVTB_CASE2(4, 4) MVTB_CASE2(4, 5)
 #undef MVTB_CASE2
@@ -334,10 +330,11 @@ __device__ __forceinline__ void fft_stage_generic(int R, cf* base, cf* scratch, 
 // MAXR bounds the radices compiled into a kernel (5: 2/3/4/5, 13: + 7/11/13, 31: all): each unrolled prime
 // stage is P^2 FMAs of code, so kernels for axes without big primes are instantiated without them.
 template <bool INV, bool SEQ_FAST, int MAXR>
-__device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, cf* scratch, int seq_stride, int elem_stride, int count,
-                                                   int n, int L, const cf* __restrict__ tw, int tid, int nthr) {
+__device__ __forceinline__ void fft_stage_dispatch(cf* base, cf* scratch, int seq_stride, int elem_stride, int count, int n,
+                                                   const PassDev& ps, const cf* __restrict__ tw, const TaskMap& tm, int tid, int nthr) {
+    const int R = ps.r1;
     switch (R) {
-#define MVTB_CASE(RR) case RR: fft_stage<RR, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, n, L, tw, tid, nthr); break;
+#define MVTB_CASE(RR) case RR: fft_stage<RR, INV, SEQ_FAST>(base, seq_stride, elem_stride, count, ps, tw, tm, tid, nthr); break;
         MVTB_CASE(2) MVTB_CASE(3) MVTB_CASE(4) MVTB_CASE(5)
         default:
             if (MAXR > 5) {
@@ -348,7 +345,7 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, cf* scratch,
                             switch (R) {
                                 MVTB_CASE(17) MVTB_CASE(19) MVTB_CASE(23) MVTB_CASE(29) MVTB_CASE(31)
                                 default:
-                                    if (scratch) fft_stage_generic<INV, SEQ_FAST>(R, base, scratch, seq_stride, elem_stride, count, n, L, tw, tid, nthr);
+                                    if (scratch) fft_stage_generic<INV, SEQ_FAST>(R, base, scratch, seq_stride, elem_stride, count, n, ps.L, tw, tid, nthr);
                                     break;
                             }
                         }
@@ -360,23 +357,23 @@ __device__ __forceinline__ void fft_stage_dispatch(int R, cf* base, cf* scratch,
     }
 }
 
-// Whole transform; the caller has synchronised before, and a __syncthreads() follows every (fused) stage.
-// ax.fuse[s] = 1 marks stage s as fused with stage s+1 (set at plan creation, never overlapping).
+template <bool SEQ_FAST>
+__device__ __forceinline__ TaskMap fft_task_map(int count, int tid, int nthr) {
+    TaskMap tm;
+    tm.sq = 0; tm.b0 = 0; tm.bstep = 1;
+    if (SEQ_FAST) { tm.sq = tid % count; tm.b0 = tid / count; tm.bstep = nthr / count; }
+    return tm;
+}
+
+// Whole transform; the caller has synchronised before, and a __syncthreads() follows every pass.
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr, cf* scratch = nullptr) {
-    int L = ax.n;
-    for (int s = 0; s < ax.nstage; ++s) {
-        const int R = ax.radix[s];
-        if (ax.fuse[s]) {
-            const int R2 = ax.radix[s + 1];
-            fft_stage2_dispatch<false, SEQ_FAST>(R, R2, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
-            L /= R * R2;
-            ++s;
-        } else {
-            fft_stage_dispatch<false, SEQ_FAST, MAXR>(R, base, scratch, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
-            L /= R;
-        }
+    const TaskMap tm = fft_task_map<SEQ_FAST>(count, tid, nthr);
+    for (int s = 0; s < ax.npass; ++s) {
+        const PassDev& ps = ax.pass[s];
+        if (ps.r2) fft_stage2_dispatch<false, SEQ_FAST>(base, seq_stride, elem_stride, count, ps, ax.tw, tm, tid, nthr);
+        else fft_stage_dispatch<false, SEQ_FAST, MAXR>(base, scratch, seq_stride, elem_stride, count, ax.n, ps, ax.tw, tm, tid, nthr);
         __syncthreads();
     }
 }
@@ -384,18 +381,11 @@ __device__ __forceinline__ void fft_forward(const AxisDev& ax, cf* base, int seq
 template <bool SEQ_FAST, int MAXR>
 __device__ __forceinline__ void fft_inverse(const AxisDev& ax, cf* base, int seq_stride, int elem_stride, int count,
                                             int tid, int nthr, cf* scratch = nullptr) {
-    int L = 1;                                   // block length of the stages already undone
-    for (int s = ax.nstage - 1; s >= 0; --s) {
-        const int R = ax.radix[s];
-        if (s > 0 && ax.fuse[s - 1]) {
-            const int R1 = ax.radix[s - 1];
-            L *= R * R1;
-            fft_stage2_dispatch<true, SEQ_FAST>(R1, R, base, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
-            --s;
-        } else {
-            L *= R;
-            fft_stage_dispatch<true, SEQ_FAST, MAXR>(R, base, scratch, seq_stride, elem_stride, count, ax.n, L, ax.tw, tid, nthr);
-        }
+    const TaskMap tm = fft_task_map<SEQ_FAST>(count, tid, nthr);
+    for (int s = ax.npass - 1; s >= 0; --s) {
+        const PassDev& ps = ax.pass[s];
+        if (ps.r2) fft_stage2_dispatch<true, SEQ_FAST>(base, seq_stride, elem_stride, count, ps, ax.tw, tm, tid, nthr);
+        else fft_stage_dispatch<true, SEQ_FAST, MAXR>(base, scratch, seq_stride, elem_stride, count, ax.n, ps, ax.tw, tm, tid, nthr);
         __syncthreads();
     }
 }

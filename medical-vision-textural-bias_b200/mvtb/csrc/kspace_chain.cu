@@ -104,29 +104,36 @@ k_rows_fwd(const float* __restrict__ in, cf* __restrict__ ws, AxisDev ax, int nh
     long long rem = n_pairs - pair0;
     const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
 
-    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;          // one warp per row pair: no divisions, coalesced rows
+    // One warp per row pair, no divisions.  The rows go global -> shared as 4-byte asynchronous copies (row a into
+    // the real parts, row b into the imaginary parts), all of them in flight at once.
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
     for (int rp = wid; rp < np; rp += nw) {
         const long long ra = 2 * (pair0 + rp);
         const float* pa = in + ra * n;
         const bool hasb = ra + 1 < n_rows;
         cf* sr = s + rp * pitch;
-        for (int j = lane; j < n; j += 32) sr[j] = cmk(pa[j], hasb ? pa[n + j] : 0.f);
+        for (int j = lane; j < n; j += 32) {
+            cp_async<4>(&sr[j].x, pa + j);
+            if (hasb) cp_async<4>(&sr[j].y, pa + n + j);
+            else sr[j].y = 0.f;
+        }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr);
 
     // Z = FFT(a + i b):  A[k] = (Z[k] + conj Z[n-k]) / 2,  B[k] = (Z[k] - conj Z[n-k]) / (2i)
-    for (int rp = wid; rp < np; rp += nw) {
-        const long long ra = 2 * (pair0 + rp);
-        const bool hasb = ra + 1 < n_rows;
-        const cf* sr = s + rp * pitch;
-        cf* wa = ws + ra * nh;
-        for (int k = lane; k < nh; k += 32) {
-            const int kn = k == 0 ? 0 : n - k;
-            const cf zk = sr[__ldg(ax.k2pos + k)];
-            const cf zn = sr[__ldg(ax.k2pos + kn)];
+    // lanes own bins (positions looked up once), the warp walks its row pairs
+    for (int k = lane; k < nh; k += 32) {
+        const int pk = __ldg(ax.k2pos + k), pn = __ldg(ax.k2pos + (k == 0 ? 0 : n - k));
+        for (int rp = wid; rp < np; rp += nw) {
+            const long long ra = 2 * (pair0 + rp);
+            const cf* sr = s + rp * pitch;
+            const cf zk = sr[pk], zn = sr[pn];
+            cf* wa = ws + ra * nh;
             wa[k] = cmk(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-            if (hasb) wa[nh + k] = cmk(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+            if (ra + 1 < n_rows) wa[nh + k] = cmk(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
         }
     }
 }
@@ -146,16 +153,19 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
 
     // Z[k] = A[k] + i B[k];  Z[n-k] = conj A[k] + i conj B[k]
     const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-    for (int rp = wid; rp < np; rp += nw) {
-        const long long ra = 2 * (pair0 + rp);
-        const bool hasb = ra + 1 < n_rows;
-        const cf* wa = ws + ra * nh;
-        cf* sr = s + rp * pitch;
-        for (int k = lane; k < nh; k += 32) {
+    for (int k = lane; k < nh; k += 32) {
+        const int pk = __ldg(ax.k2pos + k);
+        const bool mirror = k != 0 && 2 * k != n;
+        const int pn = mirror ? __ldg(ax.k2pos + (n - k)) : 0;
+        MVTB_UNROLL_N(4)
+        for (int rp = wid; rp < np; rp += nw) {
+            const long long ra = 2 * (pair0 + rp);
+            const cf* wa = ws + ra * nh;
             const cf A = wa[k];
-            const cf B = hasb ? wa[nh + k] : cmk(0.f, 0.f);
-            sr[__ldg(ax.k2pos + k)] = cmk(A.x - B.y, A.y + B.x);
-            if (k != 0 && 2 * k != n) sr[__ldg(ax.k2pos + (n - k))] = cmk(A.x + B.y, B.x - A.y);
+            const cf B = (ra + 1 < n_rows) ? wa[nh + k] : cmk(0.f, 0.f);
+            cf* sr = s + rp * pitch;
+            sr[pk] = cmk(A.x - B.y, A.y + B.x);
+            if (mirror) sr[pn] = cmk(A.x + B.y, B.x - A.y);
         }
     }
     __syncthreads();
@@ -226,19 +236,38 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     const bool col_ok = i0 + t < inner;
     const long long gstep = (long long)(nthr >> lgT) * inner;
 
-    {
+    {   // the whole tile in flight at once: 8-byte asynchronous copies, no registers held
         const cf* gp = base + (long long)(tid >> lgT) * inner + t;
-        MVTB_UNROLL_N(4)
-        for (int e = tid; e < n * T; e += nthr, gp += gstep) s[e] = col_ok ? *gp : cmk(0.f, 0.f);
+        if (col_ok) {
+            for (int e = tid; e < n * T; e += nthr, gp += gstep) cp_async<8>(s + e, gp);
+        } else {
+            for (int e = tid; e < n * T; e += nthr) s[e] = cmk(0.f, 0.f);
+        }
+        cp_async_commit();
     }
-    __syncthreads();
 
     cf* scratch = ax.generic ? s + (size_t)n * T : nullptr;
-    if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
 
+    // ---- pointwise stage, part 1 (while the tile is still in flight): what depends only on the bin along this
+    // axis goes into a shared table, what depends only on the column into registers.
+    int4* tab = nullptr;                   // per position j: (shifted index, mask term at +f, mask term at -f, odd)
+    long long qp = 0, qn = 0;
+    float wgt = g.scale;
+    unsigned mpos = 0, mneg = 0;           // per-spike "all lower axes match" bits
     if (MODE == AX_MID) {
         const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
-        // ---- per-column part: axes below this one
+        tab = (int4*)(smem_raw + (((size_t)n * T * sizeof(cf) * (ax.generic ? 2 : 1)) + 15) / 16 * 16);
+        const bool masked = d.mask_kind != MVTB_MASK_NONE && axis < d.mask_ndim;
+        for (int j = tid; j < n; j += nthr) {
+            const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
+            const int imn = (2 * (n / 2) - im + n) % n;
+            int4 e;
+            e.x = im;
+            e.y = masked ? (int)mask_term(d.mask_kind, im, n) : 0;      // < (2n)^2 <= 2^30 for any tile that fits
+            e.z = masked ? (int)mask_term(d.mask_kind, imn, n) : 0;
+            e.w = (axis < d.wrap_naxes && (im & 1)) ? 1 : 0;
+            tab[j] = e;
+        }
         int ish[MVTB_MAX_FFT_DIMS], ineg[MVTB_MAX_FFT_DIMS];
         long long rest = i0 + t;
         {
@@ -247,13 +276,10 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             ish[0] = (k0 + g.shape[0] / 2) % g.shape[0];
         }
         for (int b = 1; b < axis; ++b) {
-            const int p = (int)(rest % g.shape[b]);
+            const int pb = (int)(rest % g.shape[b]);
             rest /= g.shape[b];
-            ish[b] = (__ldg(g.pos2k[b] + p) + g.shape[b] / 2) % g.shape[b];
+            ish[b] = (__ldg(g.pos2k[b] + pb) + g.shape[b] / 2) % g.shape[b];
         }
-        long long qp = 0, qn = 0;
-        float wgt = g.scale;
-        unsigned mpos = 0, mneg = 0;       // per-spike "all lower axes match" bits
         for (int b = 0; b < axis; ++b) {
             const int nb = g.shape[b];
             ineg[b] = (2 * (nb / 2) - ish[b] + nb) % nb;
@@ -264,30 +290,38 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             if (b < d.wrap_naxes && (ish[b] & 1)) wgt *= d.wrap_alpha;
         }
         for (int sI = 0; sI < d.n_spikes; ++sI) {
-            bool p = true, q = true;
+            bool pm = true, qm = true;
             for (int b = 0; b < axis; ++b) {
-                p = p && (ish[b] == d.sp[sI].idx[b]);
-                q = q && (ineg[b] == d.sp[sI].idx[b]);
+                pm = pm && (ish[b] == d.sp[sI].idx[b]);
+                qm = qm && (ineg[b] == d.sp[sI].idx[b]);
             }
-            mpos |= (p ? 1u : 0u) << sI;
-            mneg |= (q ? 1u : 0u) << sI;
+            mpos |= (pm ? 1u : 0u) << sI;
+            mneg |= (qm ? 1u : 0u) << sI;
         }
-        // ---- per-bin part
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
+
+    if (MODE == AX_MID) {
+        const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
+        // ---- part 2: per bin
         if (col_ok) {
+            const bool any_mask = d.mask_kind != MVTB_MASK_NONE;
+            const float wodd = wgt * d.wrap_alpha;
             for (int j = tid >> lgT; j < n; j += nthr >> lgT) {
-                const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
-                const int imn = (2 * (n / 2) - im + n) % n;
+                const int4 e = tab[j];
                 float meff = 1.f;
-                if (d.mask_kind != MVTB_MASK_NONE) {
-                    long long a = qp, c = qn;
-                    if (axis < d.mask_ndim) { a += mask_term(d.mask_kind, im, n); c += mask_term(d.mask_kind, imn, n); }
-                    const int kp = (a <= d.thr ? 1 : 0) ^ d.inside_off;
-                    const int kn = (c <= d.thr ? 1 : 0) ^ d.inside_off;
+                if (any_mask) {
+                    const int kp = (qp + e.y <= d.thr ? 1 : 0) ^ d.inside_off;
+                    const int kn = (qn + e.z <= d.thr ? 1 : 0) ^ d.inside_off;
                     meff = 0.5f * (float)(kp + kn);
                 }
                 const cf K = s[j * T + t];
                 cf acc = cscale(K, meff);
                 if ((mpos | mneg) != 0u) {
+                    const int im = e.x, imn = (2 * (n / 2) - im + n) % n;
                     for (int sI = 0; sI < d.n_spikes; ++sI) {
                         const bool isp = ((mpos >> sI) & 1u) && im == d.sp[sI].idx[axis];
                         const bool isn = ((mneg >> sI) & 1u) && imn == d.sp[sI].idx[axis];
@@ -311,9 +345,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
                         }
                     }
                 }
-                float w = wgt;
-                if (axis < d.wrap_naxes && (im & 1)) w *= d.wrap_alpha;
-                s[j * T + t] = cscale(acc, w);
+                s[j * T + t] = cscale(acc, e.w ? wodd : wgt);
             }
         }
         __syncthreads();
@@ -478,7 +510,8 @@ static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const C
     const long long ntiles = (inner + T - 1) / T;
     const long long blocks = ntiles * outer;
     if (blocks > 0x7fffffffLL) { set_error("chain: grid too large"); return MVTB_EUNSUPPORTED; }
-    const size_t smem = (size_t)p->shape[axis] * T * sizeof(cf) * (p->ax[axis].generic ? 2 : 1);
+    size_t smem = (size_t)p->shape[axis] * T * sizeof(cf) * (p->ax[axis].generic ? 2 : 1);
+    if (MODE == AX_MID) smem = (smem + 15) / 16 * 16 + (size_t)p->shape[axis] * sizeof(int4);   // per-bin table of the pointwise stage
     switch (axis_maxr(p, axis)) {
         case 5: { auto kern = k_axis<MODE, 5>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
         case 13: { auto kern = k_axis<MODE, 13>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }

@@ -51,14 +51,52 @@ __device__ __forceinline__ cf cscale(cf a, float s) { return cmk(a.x * s, a.y * 
 __device__ __forceinline__ cf cmuli(cf a) { return cmk(-a.y, a.x); }    // a * (+i)
 __device__ __forceinline__ cf cmulni(cf a) { return cmk(a.y, -a.x); }   // a * (-i)
 
+// ---------------------------------------------------------------- asynchronous global -> shared copies (LDGSTS)
+// The bytes a CTA has in flight stop being limited by registers; the emulator copies synchronously.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+#ifdef MVTB_EMU
+    for (int i = 0; i < BYTES; ++i) ((unsigned char*)smem_dst)[i] = ((const unsigned char*)gsrc)[i];
+#else
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(BYTES) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) { cp_async<16>(smem_dst, gsrc); }
+__device__ __forceinline__ void cp_async_commit() {
+#ifndef MVTB_EMU
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+#ifndef MVTB_EMU
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+#endif
+}
+
 // ---------------------------------------------------------------- per-axis FFT description
 struct DescDev;
 #define MVTB_MAX_STAGES 12
+// One pass over the shared-memory tile: a radix stage, or two stages fused in registers.  Everything a thread
+// needs is precomputed on the host: with 128-thread CTAs a thread runs only a couple of butterflies per pass, so
+// per-pass integer divisions would cost as much as the butterflies.
+struct PassDev {
+    int r1, r2;                  // radices (r2 = 0: single stage)
+    int L;                       // block length entering the pass (forward order)
+    int m;                       // block length leaving it: L / (r1 * max(r2, 1))
+    int per_seq;                 // butterflies per sequence: n / (r1 * max(r2, 1))
+    int ts1, ts2;                // twiddle strides n / L and n / (L / r1)
+    unsigned magic_m, magic_ps;  // x / m = umulhi(x, magic_m), x / per_seq likewise (unused when the divisor is 1)
+};
 struct AxisDev {
     int n;                       // axis length
     int nstage;                  // radix stages
     int radix[MVTB_MAX_STAGES];  // forward (DIF) order
     int fuse[MVTB_MAX_STAGES];   // 1: stage s and s+1 run as one register-fused pass (fft_stage2)
+    int npass;
+    PassDev pass[MVTB_MAX_STAGES];
     int generic;                 // 1: some radix is a prime > 31 (fft_stage_generic: needs a scratch tile)
     const cf* tw;                // tw[t] = exp(-2 pi i t / n), t in [0, n)
     const int* pos2k;            // position after the in-place DIF  ->  frequency bin

@@ -176,6 +176,22 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
                 const int r1 = ax.radix[s], r2 = ax.radix[s + 1];
                 if (r1 <= 5 && r2 <= 5 && r1 * r2 <= 20 && r1 * r2 != 4) { ax.fuse[s] = 1; ++s; }
             }
+        ax.npass = 0;
+        for (int s = 0, L = n; s < ax.nstage; ++s) {
+            PassDev& ps = ax.pass[ax.npass++];
+            ps.r1 = ax.radix[s];
+            ps.r2 = ax.fuse[s] ? ax.radix[s + 1] : 0;
+            const int R = ps.r1 * (ps.r2 ? ps.r2 : 1);
+            ps.L = L;
+            ps.m = L / R;
+            ps.per_seq = n / R;
+            ps.ts1 = n / L;
+            ps.ts2 = ps.r2 ? n / (L / ps.r1) : 0;
+            ps.magic_m = ps.m > 1 ? 0xFFFFFFFFu / (unsigned)ps.m + 1u : 0u;
+            ps.magic_ps = ps.per_seq > 1 ? 0xFFFFFFFFu / (unsigned)ps.per_seq + 1u : 0u;
+            L /= R;
+            if (ps.r2) ++s;
+        }
         cf* tw = (cf*)(host.data() + off);
         ax.tw = (const cf*)((unsigned char*)dev + off);
         for (int t = 0; t < n; ++t) {
@@ -249,8 +265,9 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     if (p->axis_tile != 4 && p->axis_tile != 8 && p->axis_tile != 16 && p->axis_tile != 32) p->axis_tile = 16;
     for (int a = 1; a < ndim_fft; ++a) {
         const size_t gen = p->ax[a].generic ? 2 : 1;
-        while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen > smem_cap) p->axis_tile /= 2;
-        if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen > smem_cap) {
+        const size_t tabb = (size_t)p->shape[a] * 16 + 16;      // the outermost axis also holds the pointwise stage's per-bin table
+        while (p->axis_tile > 1 && (size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen + tabb > smem_cap) p->axis_tile /= 2;
+        if ((size_t)p->shape[a] * p->axis_tile * sizeof(cf) * gen + tabb > smem_cap) {
             set_error("plan_create: axis of length %d does not fit in shared memory", p->shape[a]);
             cudaFree(dev); free(p);
             return MVTB_EUNSUPPORTED;
