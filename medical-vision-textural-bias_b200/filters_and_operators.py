@@ -498,18 +498,33 @@ class KSpaceSpikeNoise(Transform, Fourier):
         else:
             pairs = [(self.loc, default if intensity is None else intensity)]
 
-        per_chan: List[List[Tuple[Tuple[int, ...], float]]] = [[] for _ in range(n_chan)]
-        for idx, val in pairs:
-            idx = tuple(int(i) for i in idx)
-            if len(idx) == rank:                      # F:975-979: one channel
-                v = val[idx[0]] if isinstance(val, _SeqABC) else val
-                per_chan[idx[0]].append((idx[1:], host.exp_f32(v)))
-            elif len(idx) == rank - 1 and rank in (3, 4):   # F:980-983: all channels
+        pairs = [(tuple(int(i) for i in idx), val) for idx, val in pairs]
+        if all(len(idx) == rank - 1 for idx, _ in pairs) and rank in (3, 4):
+            # every spike hits all channels (F:980-983): one descriptor for the whole stack, however many channels
+            shared = []
+            for idx, val in pairs:
                 if isinstance(val, _SeqABC):
                     raise TypeError("can't assign a tuple to a torch.FloatTensor")   # what F:981/983 raises
-                for c in range(n_chan):
-                    per_chan[c].append((idx, host.exp_f32(val)))
-        descs = [host.make_desc(spikes=s) for s in per_chan]
+                shared.append((idx, host.exp_f32(val)))
+            descs = [host.make_desc(spikes=shared)]
+        else:
+            per_chan: List[List[Tuple[Tuple[int, ...], float]]] = [[] for _ in range(n_chan)]
+            for idx, val in pairs:
+                if len(idx) == rank:                      # F:975-979: one channel
+                    v = val[idx[0]] if isinstance(val, _SeqABC) else val
+                    per_chan[idx[0]].append((idx[1:], host.exp_f32(v)))
+                elif len(idx) == rank - 1 and rank in (3, 4):   # F:980-983: all channels
+                    if isinstance(val, _SeqABC):
+                        raise TypeError("can't assign a tuple to a torch.FloatTensor")   # what F:981/983 raises
+                    for c in range(n_chan):
+                        per_chan[c].append((idx, host.exp_f32(val)))
+            made = {}
+            descs = []
+            for sp in per_chan:                           # channels with the same spikes share one descriptor object
+                key = tuple(sp)
+                if key not in made:
+                    made[key] = host.make_desc(spikes=sp)
+                descs.append(made[key])
         out = Fn.back(Fn.kspace_chain(x, n_dims, descs), src)
         return out if self.as_tensor_output else out.cpu().detach().numpy()
 

@@ -33,6 +33,8 @@ bool spike_fast_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_
 int spike_fast_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
                      float* minmax_out, int vols_per_sample, void* stream);
 
+int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream, void** dptr);   // plan.cu
+
 enum { AX_FWD = 0, AX_INV = 1, AX_MID = 2, AX_STATS = 3 };
 // Small CTAs, many per SM: a CTA is load -> barrier -> stages -> store with nothing overlapping inside it, so the
 // loads in flight come from having 4-6 CTAs per SM in different phases (256 threads x 2 CTAs measured 2-3x slower).
@@ -223,7 +225,7 @@ __device__ __forceinline__ cf spike_value(cf ko, float amp) {
 template <int MODE, int MAXR>
 __global__ void __launch_bounds__(128, MVTB_MINB(MAXR))
 k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int ntiles,
-       ChainGeom g, DescPack pack, double* __restrict__ sums) {
+       ChainGeom g, const DescDev* __restrict__ dv, int dshared, double* __restrict__ sums) {
     MVTB_DYN_SMEM(smem_raw);
     cf* s = (cf*)smem_raw;
     const int n = ax.n, tid = threadIdx.x, nthr = blockDim.x;
@@ -255,7 +257,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     float wgt = g.scale;
     unsigned mpos = 0, mneg = 0;           // per-spike "all lower axes match" bits
     if (MODE == AX_MID) {
-        const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
+        const DescDev& d = dv[dshared ? 0 : (int)o];
         tab = (int4*)(smem_raw + (((size_t)n * T * sizeof(cf) * (ax.generic ? 2 : 1)) + 15) / 16 * 16);
         const bool masked = d.mask_kind != MVTB_MASK_NONE && axis < d.mask_ndim;
         for (int j = tid; j < n; j += nthr) {
@@ -305,7 +307,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     if (MODE != AX_INV) fft_forward<true, MAXR>(ax, s, 1, T, T, tid, nthr, scratch);
 
     if (MODE == AX_MID) {
-        const DescDev& d = pack.d[pack.n == 1 ? 0 : (int)o];
+        const DescDev& d = dv[dshared ? 0 : (int)o];
         // ---- part 2: per bin
         if (col_ok) {
             const bool any_mask = d.mask_kind != MVTB_MASK_NONE;
@@ -447,6 +449,16 @@ static ChainGeom make_geom(const mvtb_plan* p) {
     return g;
 }
 
+static bool same_desc(const mvtb_chain_desc& a, const mvtb_chain_desc& b) {
+    if (a.mask_kind != b.mask_kind || a.mask_ndim != b.mask_ndim || a.mask_thresh != b.mask_thresh || a.inside_off != b.inside_off ||
+        a.n_spikes != b.n_spikes || a.wrap_naxes != b.wrap_naxes || memcmp(&a.wrap_alpha, &b.wrap_alpha, sizeof(float)) != 0) return false;
+    if (a.n_spikes < 0 || a.n_spikes > MVTB_MAX_SPIKES) return false;
+    for (int s = 0; s < a.n_spikes; ++s)
+        if (memcmp(a.spikes[s].idx, b.spikes[s].idx, sizeof(a.spikes[s].idx)) != 0 ||
+            memcmp(&a.spikes[s].amplitude, &b.spikes[s].amplitude, sizeof(float)) != 0) return false;
+    return true;
+}
+
 // validates one user descriptor against the plan and converts it to the device view
 int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
     memset(d, 0, sizeof(*d));
@@ -500,7 +512,7 @@ static int launch_rows_fwd(mvtb_plan* p, const float* in, cf* ws, long long n_ro
 
 template <int MODE>
 static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const ChainGeom& g,
-                       const DescPack& pack, double* sums, void* stream) {
+                       const DescDev* dv, int dshared, double* sums, void* stream) {
     ProfScope prof(p, MODE == AX_FWD ? MVTB_K_AXIS_FWD : (MODE == AX_INV ? MVTB_K_AXIS_INV : MVTB_K_AXIS_MID), stream);
     long long inner = p->nh;
     for (int b = 1; b < axis; ++b) inner *= p->shape[b];
@@ -513,9 +525,9 @@ static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const C
     size_t smem = (size_t)p->shape[axis] * T * sizeof(cf) * (p->ax[axis].generic ? 2 : 1);
     if (MODE == AX_MID) smem = (smem + 15) / 16 * 16 + (size_t)p->shape[axis] * sizeof(int4);   // per-bin table of the pointwise stage
     switch (axis_maxr(p, axis)) {
-        case 5: { auto kern = k_axis<MODE, 5>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
-        case 13: { auto kern = k_axis<MODE, 13>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
-        default: { auto kern = k_axis<MODE, 31>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, pack, sums); break; }
+        case 5: { auto kern = k_axis<MODE, 5>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, dv, dshared, sums); break; }
+        case 13: { auto kern = k_axis<MODE, 13>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, dv, dshared, sums); break; }
+        default: { auto kern = k_axis<MODE, 31>; MVTB_LAUNCH(kern, dim3((unsigned)blocks), dim3(kThreads), smem, stream, ws, p->ax[axis], axis, inner, T, (int)ntiles, g, dv, dshared, sums); break; }
     }
     return MVTB_OK;
 }
@@ -550,22 +562,17 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
         desc = shifted.data();
     }
 
+    // identical per-volume descriptors (one spike location for a whole slice stack, F:982-983) are one descriptor
+    if (n_desc > 1) {
+        bool same = true;
+        for (int v = 1; v < n_desc && same; ++v) same = same_desc(desc[0], desc[v]);
+        if (same) n_desc = 1;
+    }
     const ChainGeom g = make_geom(p);
-    DescPack pack;
-    memset(&pack, 0, sizeof(pack));
-    DescPack none;
-    memset(&none, 0, sizeof(none));
-    none.n = 1;
-    if (n_desc == 1) {
-        pack.n = 1;
-        int rc = convert_desc(p, desc, &pack.d[0]);
+    std::vector<DescDev> hdesc((size_t)n_desc);
+    for (int v = 0; v < n_desc; ++v) {                 // validate everything before launching anything
+        int rc = convert_desc(p, desc + v, &hdesc[v]);
         if (rc != MVTB_OK) return rc;
-    } else {
-        DescDev tmp;
-        for (int v = 0; v < n_volumes; ++v) {          // validate everything before launching anything
-            int rc = convert_desc(p, desc + v, &tmp);
-            if (rc != MVTB_OK) return rc;
-        }
     }
     long long rows_per_vol = 1;
     for (int a = 1; a < p->ndim; ++a) rows_per_vol *= p->shape[a];
@@ -581,6 +588,13 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
     if (bl_eligible(p, desc, n_desc, &blF))
         return bl_chain(p, in, out, n_volumes, desc, n_desc, blF, minmax_out, vols_per_sample, stream);
 
+    const DescDev* ddesc = nullptr;                    // device copy of the converted descriptors, valid on `stream`
+    {
+        void* dvp = nullptr;
+        int rc = plan_stage_upload(p, hdesc.data(), hdesc.size() * sizeof(DescDev), stream, &dvp);
+        if (rc != MVTB_OK) return rc;
+        ddesc = (const DescDev*)dvp;
+    }
     const int mid = p->ndim - 1;
     for (int v0 = 0; v0 < n_volumes; v0 += p->chunk) {
         const int nv = (n_volumes - v0 < p->chunk) ? (n_volumes - v0) : p->chunk;
@@ -588,23 +602,13 @@ extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, 
         int rc = launch_rows_fwd(p, in + (size_t)v0 * p->vol_real, p->ws, n_rows, stream);
         if (rc != MVTB_OK) return rc;
         for (int a = 1; a < mid; ++a) {
-            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, none, nullptr, stream);
+            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, nullptr, 1, nullptr, stream);
             if (rc != MVTB_OK) return rc;
         }
-        if (n_desc == 1) {
-            rc = launch_axis<AX_MID>(p, p->ws, mid, nv, g, pack, nullptr, stream);
-            if (rc != MVTB_OK) return rc;
-        } else {
-            for (int w0 = 0; w0 < nv; w0 += MVTB_DESC_PACK) {
-                const int nw = (nv - w0 < MVTB_DESC_PACK) ? (nv - w0) : MVTB_DESC_PACK;
-                pack.n = nw == 1 ? 1 : nw;
-                for (int i = 0; i < nw; ++i) convert_desc(p, desc + v0 + w0 + i, &pack.d[i]);
-                rc = launch_axis<AX_MID>(p, p->ws + (size_t)w0 * p->vol_half, mid, nw, g, pack, nullptr, stream);
-                if (rc != MVTB_OK) return rc;
-            }
-        }
+        rc = launch_axis<AX_MID>(p, p->ws, mid, nv, g, ddesc + (n_desc == 1 ? 0 : v0), n_desc == 1 ? 1 : 0, nullptr, stream);
+        if (rc != MVTB_OK) return rc;
         for (int a = mid - 1; a >= 1; --a) {
-            rc = launch_axis<AX_INV>(p, p->ws, a, nv, g, none, nullptr, stream);
+            rc = launch_axis<AX_INV>(p, p->ws, a, nv, g, nullptr, 1, nullptr, stream);
             if (rc != MVTB_OK) return rc;
         }
         {
@@ -641,9 +645,6 @@ extern "C" int mvtb_kspace_logabs_sum_f32(mvtb_plan* p, const float* in, int n_v
     MVTB_CUDA(cudaSetDevice(p->device));
     MVTB_CUDA(cudaMemsetAsync(sums_out, 0, sizeof(double) * (size_t)n_volumes, (cudaStream_t)stream));
     const ChainGeom g = make_geom(p);
-    DescPack none;
-    memset(&none, 0, sizeof(none));
-    none.n = 1;
     long long rows_per_vol = 1;
     for (int a = 1; a < p->ndim; ++a) rows_per_vol *= p->shape[a];
     const int mid = p->ndim - 1;
@@ -652,10 +653,10 @@ extern "C" int mvtb_kspace_logabs_sum_f32(mvtb_plan* p, const float* in, int n_v
         int rc = launch_rows_fwd(p, in + (size_t)v0 * p->vol_real, p->ws, rows_per_vol * nv, stream);
         if (rc != MVTB_OK) return rc;
         for (int a = 1; a < mid; ++a) {
-            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, none, nullptr, stream);
+            rc = launch_axis<AX_FWD>(p, p->ws, a, nv, g, nullptr, 1, nullptr, stream);
             if (rc != MVTB_OK) return rc;
         }
-        rc = launch_axis<AX_STATS>(p, p->ws, mid, nv, g, none, sums_out + v0, stream);
+        rc = launch_axis<AX_STATS>(p, p->ws, mid, nv, g, nullptr, 1, sums_out + v0, stream);
         if (rc != MVTB_OK) return rc;
     }
     MVTB_CUDA(cudaGetLastError());

@@ -346,8 +346,14 @@ int spike_fast_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, c
     int chunk = (int)(p->ws_bytes / need);
     if (chunk < 1) { set_error("spike fast path: workspace too small"); return MVTB_EUNSUPPORTED; }
     if (chunk > n_volumes) chunk = n_volumes;
-    // 16 volumes per round: enough CTAs to hide the two one-CTA-per-volume helper kernels
-    if (chunk > 16) chunk = 16;
+    // ~16 BraTS volumes' worth of voxels per round: enough CTAs to hide the two one-CTA-per-volume helper kernels,
+    // and thousands of 2-D slices per round rather than 16 (a stack of 8192 240x240 slices is 4 rounds, not 512)
+    {
+        long long cap = (16LL * 240 * 240 * 155) / (long long)p->vol_real;
+        if (cap < 16) cap = 16;
+        if (cap > 65535) cap = 65535;                  // grid.y
+        if (chunk > cap) chunk = (int)cap;
+    }
     cf* w_partial = p->ws;
     cf* w_delta = w_partial + (size_t)chunk * MVTB_MAX_SPIKES * ctas;
     cf* w_tab = w_delta + (size_t)chunk * MVTB_MAX_SPIKES;

@@ -162,6 +162,22 @@ def test_emu_chunking_and_per_volume_descs():
         assert mm[2 * s] == blk.min() and mm[2 * s + 1] == blk.max()
 
 
+def test_emu_general_path_many_per_volume_descs_and_identical_descs():
+    """General FFT path (GibbsNoise mask: not band-limited) with one descriptor per volume for more volumes than a
+    chunk holds, so descriptors are indexed by volume across chunks; and n identical descriptors == one descriptor."""
+    shape = (11, 6, 5, 9)                                     # 11 volumes of 6x5x9
+    x = P.synthetic_volume(22, shape).numpy()
+    alphas = [0.15 + 0.07 * c for c in range(11)]
+    descs = [host.make_desc(mask_kind=B.MASK_CENTRED, mask_ndim=3, mask_thresh=host.gibbs_threshold(a, shape[1:])) for a in alphas]
+    y, _ = emu.chain(x, 3, descs, chunk=4)
+    for c in range(11):
+        want = P.gibbs_noise(torch.from_numpy(x[c:c + 1]), alphas[c]).numpy()
+        assert rel_l2(y[c:c + 1], want) <= TOL, c
+    y1, _ = emu.chain(x, 3, [descs[3]], chunk=4)
+    yn, _ = emu.chain(x, 3, [descs[3]] * 11, chunk=4)
+    assert np.array_equal(y1, yn)
+
+
 @pytest.mark.parametrize("name", golden_names("sap_"))
 def test_emu_salt_pepper_injected_uniforms_bit_exact(name):
     m, z = load_golden(name)
