@@ -155,19 +155,65 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
 
     // Z[k] = A[k] + i B[k];  Z[n-k] = conj A[k] + i conj B[k]
     const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-    for (int k = lane; k < nh; k += 32) {
-        const int pk = __ldg(ax.k2pos + k);
-        const bool mirror = k != 0 && 2 * k != n;
-        const int pn = mirror ? __ldg(ax.k2pos + (n - k)) : 0;
-        MVTB_UNROLL_N(4)
+    constexpr int KMAX = 8;                      // bins per lane held in registers by the staged variant
+    if (nh <= 32 * KMAX && 2 * nh <= pitch) {
+        // Stage the two half-spectrum rows of every pair in the pair's own tile row (A at 0.., B at nh..) with
+        // asynchronous copies, all in flight at once; then each warp combines its pairs in place: all of a pair's
+        // bins are read into registers before any position is written.
         for (int rp = wid; rp < np; rp += nw) {
             const long long ra = 2 * (pair0 + rp);
             const cf* wa = ws + ra * nh;
-            const cf A = wa[k];
-            const cf B = (ra + 1 < n_rows) ? wa[nh + k] : cmk(0.f, 0.f);
             cf* sr = s + rp * pitch;
-            sr[pk] = cmk(A.x - B.y, A.y + B.x);
-            if (mirror) sr[pn] = cmk(A.x + B.y, B.x - A.y);
+            const bool hasb = ra + 1 < n_rows;
+            for (int k = lane; k < nh; k += 32) {
+                cp_async<8>(sr + k, wa + k);
+                if (hasb) cp_async<8>(sr + nh + k, wa + nh + k);
+                else sr[nh + k] = cmk(0.f, 0.f);
+            }
+        }
+        cp_async_commit();
+        int pk[KMAX], pn[KMAX];
+        MVTB_UNROLL
+        for (int i = 0; i < KMAX; ++i) {
+            const int k = lane + 32 * i;
+            pk[i] = k < nh ? __ldg(ax.k2pos + k) : 0;
+            pn[i] = (k < nh && k != 0 && 2 * k != n) ? __ldg(ax.k2pos + (n - k)) : -1;
+        }
+        cp_async_wait<0>();
+        __syncwarp();                            // a pair is staged and combined by the same warp
+        for (int rp = wid; rp < np; rp += nw) {
+            cf* sr = s + rp * pitch;
+            cf A[KMAX], B[KMAX];
+            MVTB_UNROLL
+            for (int i = 0; i < KMAX; ++i) {
+                const int k = lane + 32 * i;
+                if (k < nh) { A[i] = sr[k]; B[i] = sr[nh + k]; }
+            }
+            __syncwarp();
+            MVTB_UNROLL
+            for (int i = 0; i < KMAX; ++i) {
+                const int k = lane + 32 * i;
+                if (k < nh) {
+                    sr[pk[i]] = cmk(A[i].x - B[i].y, A[i].y + B[i].x);
+                    if (pn[i] >= 0) sr[pn[i]] = cmk(A[i].x + B[i].y, B[i].x - A[i].y);
+                }
+            }
+        }
+    } else {
+        for (int k = lane; k < nh; k += 32) {
+            const int pk = __ldg(ax.k2pos + k);
+            const bool mirror = k != 0 && 2 * k != n;
+            const int pn = mirror ? __ldg(ax.k2pos + (n - k)) : 0;
+            MVTB_UNROLL_N(4)
+            for (int rp = wid; rp < np; rp += nw) {
+                const long long ra = 2 * (pair0 + rp);
+                const cf* wa = ws + ra * nh;
+                const cf A = wa[k];
+                const cf B = (ra + 1 < n_rows) ? wa[nh + k] : cmk(0.f, 0.f);
+                cf* sr = s + rp * pitch;
+                sr[pk] = cmk(A.x - B.y, A.y + B.x);
+                if (mirror) sr[pn] = cmk(A.x + B.y, B.x - A.y);
+            }
         }
     }
     __syncthreads();

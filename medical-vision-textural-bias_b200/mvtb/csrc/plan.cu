@@ -225,17 +225,48 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->table_mem = dev;
 
     // ---- kernel geometry
+    // Row pitch of the rows kernels' tile (complex elements): at least 2 nh (the inverse kernel stages a pair of
+    // half-spectrum rows in one tile row), and among the next 32 values the one with the fewest shared-memory bank
+    // conflicts: for every pass, the 8-byte accesses of the first 128 tasks are binned per half-warp into the 16
+    // bank pairs; a half-warp costs its fullest bin.  (155 = 5 x 31: pitch 157 put consecutive sequences 13 bank
+    // pairs apart, so the 5-wide groups of the radix-31 pass overlapped two by two.)
     int pitch = 2 * p->nh;
-    if ((pitch & 1) == 0) ++pitch;
+    {
+        const AxisDev& ax0 = p->ax[0];
+        long long best = -1;
+        for (int cand = 2 * p->nh; cand < 2 * p->nh + 32; ++cand) {
+            long long cost = 0;
+            for (int s = 0; s < ax0.npass; ++s) {
+                const PassDev& ps = ax0.pass[s];
+                const int R = ps.r1 * (ps.r2 ? ps.r2 : 1);
+                long long pass_cost = 0;
+                for (int half = 0; half < 8; ++half) {
+                    int bins[16] = {0};
+                    int worst = 0;
+                    for (int l = 0; l < 16; ++l) {
+                        const int task = half * 16 + l;
+                        const int sq = task / ps.per_seq, b = task % ps.per_seq;
+                        const int blk = b / ps.m, j = b % ps.m;
+                        const int addr = sq * cand + blk * ps.L + j;
+                        const int v = ++bins[addr & 15];
+                        worst = v > worst ? v : worst;
+                    }
+                    pass_cost += worst;
+                }
+                cost += pass_cost * R;
+            }
+            if (best < 0 || cost < best) { best = cost; pitch = cand; }
+        }
+    }
     p->row_pitch = pitch;
     const size_t smem_cap = (size_t)prop.sharedMemPerBlockOptin;
     const size_t gen0 = p->ax[0].generic ? 2 : 1;              // generic stages need a scratch copy of the tile
     size_t per_pair = (size_t)pitch * sizeof(cf) * gen0;
-    // Row pairs per CTA (kernels run 128 threads): at most ~32 KB of tile so that several CTAs share an SM, and
+    // Row pairs per CTA (kernels run 128 threads): at most ~36 KB of tile so that several CTAs share an SM, and
     // among those sizes the one that wastes the fewest thread slots in the stage passes, weighting a pass by its
     // radix (5 x 31 = 155: the radix-31 pass has 5 butterflies per pair, so 25 pairs fill 125 of 128 threads
     // where 26 would need a second, almost empty round).
-    int rp_cap = (int)((size_t)32 * 1024 / per_pair);
+    int rp_cap = (int)((size_t)36 * 1024 / per_pair);
     if (rp_cap > 64) rp_cap = 64;
     if (rp_cap < 1) rp_cap = 1;
     int rp = rp_cap;
