@@ -798,6 +798,7 @@ static int bl_configure_nf(int optin) {
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2) MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MVTB_OK;
 }
 #endif

@@ -621,61 +621,102 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     }
     __syncthreads();
 
-    // ---- D axis: B[jw][jd] = sum_d G[jw][d] exp(-2 pi i fd d / D), then the pointwise stage
+    // ---- D axis forward, pair-folded like the other axes: with e = G[d] + G[D-d], o = G[d] - G[D-d] (in place),
+    //   B(+-fd) = G[0] (+ G[D/2] (-1)^fd) + P -+ iQ,   P = sum_d e cos(2 pi fd d / D),  Q = sum_d o sin(2 pi fd d / D)
+    const int dpairs = (D - 1) / 2;
+    for (int o = tid; o < K * dpairs; o += nthr) {
+        const int jw = o / dpairs, dd = o - jw * dpairs + 1;
+        cf* row = sg + jw * D;
+        const cf a = row[dd], b = row[D - dd];
+        row[dd] = cadd(a, b);
+        row[D - dd] = csub(a, b);
+    }
+    __syncthreads();
     {
         const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
         int shape[3];
         shape[0] = g.D; shape[1] = g.W; shape[2] = g.H;
-        for (int o = tid; o < K * K; o += nthr) {
-            const int jw = o / K, jd = o - jw * K;
-            const int fd = jd - F;
-            const int step = ((fd % D) + D) % D;
+        for (int o = tid; o < K * (F + 1); o += nthr) {
+            const int jw = o / (F + 1), fd = o - jw * (F + 1);
             const cf* row = sg + jw * D;
-            cf acc = cmk(0.f, 0.f);
+            cf P = cmk(0.f, 0.f), Qs = cmk(0.f, 0.f);
             int idx = 0;
-            for (int d = 0; d < D; ++d) {
-                const cf a = row[d], w_ = st[idx];
-                acc.x = fmaf(a.x, w_.x, fmaf(-a.y, w_.y, acc.x));
-                acc.y = fmaf(a.x, w_.y, fmaf(a.y, w_.x, acc.y));
-                idx += step;
+            for (int dd = 1; dd <= dpairs; ++dd) {
+                idx += fd;
                 if (idx >= D) idx -= D;
+                const cf e = row[dd], od = row[D - dd], w_ = st[idx];     // w_ = (cos, -sin)
+                P.x = fmaf(e.x, w_.x, P.x);
+                P.y = fmaf(e.y, w_.x, P.y);
+                Qs.x = fmaf(od.x, -w_.y, Qs.x);
+                Qs.y = fmaf(od.y, -w_.y, Qs.y);
             }
+            cf base = row[0];
+            if ((D & 1) == 0) {
+                const cf gn = row[D / 2];
+                base = (fd & 1) ? csub(base, gn) : cadd(base, gn);
+            }
+            P = cadd(P, base);
             int ish[3];
-            ish[0] = fd + D / 2;
             ish[1] = (jw - F) + g.W / 2;
             ish[2] = fh + g.H / 2;
-            sb[o] = pointwise_bin(bv.d, 3, shape, ish, acc, g.scale);
+            ish[0] = fd + D / 2;
+            sb[jw * K + F + fd] = pointwise_bin(bv.d, 3, shape, ish, cmk(P.x + Qs.y, P.y - Qs.x), g.scale);     // P - iQ
+            if (fd > 0) {
+                ish[0] = -fd + D / 2;
+                sb[jw * K + F - fd] = pointwise_bin(bv.d, 3, shape, ish, cmk(P.x - Qs.y, P.y + Qs.x), g.scale); // P + iQ
+            }
         }
+    }
+    __syncthreads();
+    // E = B(+fd) + B(-fd), O = B(+fd) - B(-fd) packed as float4 over the now free G tile: the way back along D is
+    //   G'[j][d] = B(0) + sum_fd ( E cos(2 pi fd d / D) + i O sin(2 pi fd d / D) )
+    float4* seo = (float4*)sg;                            // [K][F + 1]; entry 0 of a row holds (B(0), 0)
+    for (int o = tid; o < K * (F + 1); o += nthr) {
+        const int jw = o / (F + 1), fd = o - jw * (F + 1);
+        const cf bp = sb[jw * K + F + fd], bm = sb[jw * K + F - fd];
+        seo[o] = fd == 0 ? make_float4(bp.x, bp.y, 0.f, 0.f) : make_float4(bp.x + bm.x, bp.y + bm.y, bp.x - bm.x, bp.y - bm.y);
     }
     __syncthreads();
 
     // ---- back along D (into registers) and along W (streamed out in place)
     for (int d = tid; d < D; d += nthr) {
-        // G'[j][d] = sum_jd B[j][jd] exp(+2 pi i fd d / D); keep S_f = G'(+f) + G'(-f), T_f = G'(+f) - G'(-f)
-        float2 stx[NF], sty[NF];
-        const int idx0 = (int)((((long long)(-F) * d) % D + D) % D);
+        // gp[f] = G'[F + f][d], gm[f] = G'[F - f][d]; the W axis then needs S_f = gp + gm, T_f = gp - gm
+        cf gp[NF], gm[NF];
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) {
-            stx[f] = make_float2(0.f, 0.f);
-            sty[f] = make_float2(0.f, 0.f);
+            gp[f] = cmk(0.f, 0.f);
+            gm[f] = cmk(0.f, 0.f);
             if (f <= F) {
-                cf gp = cmk(0.f, 0.f), gm = cmk(0.f, 0.f);
-                int idx = idx0;
-                const cf* bp = sb + (F + f) * K;
-                const cf* bm = sb + (F - f) * K;
-                for (int jd = 0; jd < K; ++jd) {
-                    const cf w_ = st[idx];                 // conj(w_) = exp(+...)
-                    const cf b1 = bp[jd], b2 = bm[jd];
-                    gp.x = fmaf(b1.x, w_.x, fmaf(b1.y, w_.y, gp.x));
-                    gp.y = fmaf(b1.y, w_.x, fmaf(-b1.x, w_.y, gp.y));
-                    gm.x = fmaf(b2.x, w_.x, fmaf(b2.y, w_.y, gm.x));
-                    gm.y = fmaf(b2.y, w_.x, fmaf(-b2.x, w_.y, gm.y));
-                    idx += d;
-                    if (idx >= D) idx -= D;
-                }
-                if (f == 0) { stx[0] = make_float2(gp.x, 0.f); sty[0] = make_float2(gp.y, 0.f); }
-                else { stx[f] = make_float2(gp.x + gm.x, gp.x - gm.x); sty[f] = make_float2(gp.y + gm.y, gp.y - gm.y); }
+                const float4 e0 = seo[(F + f) * (F + 1)], e1 = seo[(F - f) * (F + 1)];
+                gp[f] = cmk(e0.x, e0.y);
+                gm[f] = cmk(e1.x, e1.y);
             }
+        }
+        int idx = 0;
+        for (int fd = 1; fd <= F; ++fd) {
+            idx += d;
+            if (idx >= D) idx -= D;
+            const cf w_ = st[idx];                        // (cos, -sin) of 2 pi fd d / D
+            const float c = w_.x, sn = -w_.y;
+            MVTB_UNROLL
+            for (int f = 0; f < NF; ++f) {
+                if (f <= F) {
+                    const float4 eo = seo[(F + f) * (F + 1) + fd];
+                    gp[f].x = fmaf(eo.x, c, fmaf(-eo.w, sn, gp[f].x));
+                    gp[f].y = fmaf(eo.y, c, fmaf(eo.z, sn, gp[f].y));
+                    if (f > 0) {
+                        const float4 em = seo[(F - f) * (F + 1) + fd];
+                        gm[f].x = fmaf(em.x, c, fmaf(-em.w, sn, gm[f].x));
+                        gm[f].y = fmaf(em.y, c, fmaf(em.z, sn, gm[f].y));
+                    }
+                }
+            }
+        }
+        float2 stx[NF], sty[NF];
+        MVTB_UNROLL
+        for (int f = 0; f < NF; ++f) {
+            if (f == 0) { stx[0] = make_float2(gp[0].x, 0.f); sty[0] = make_float2(gp[0].y, 0.f); }
+            else { stx[f] = make_float2(gp[f].x + gm[f].x, gp[f].x - gm[f].x); sty[f] = make_float2(gp[f].y + gm[f].y, gp[f].y - gm[f].y); }
         }
         cf* yv = yplane + d;
         {
