@@ -34,9 +34,10 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 SHAPE = (240, 240, 155)
-# in-kernel S&P sampler: one Philox uniform per voxel (default; 7.9 us/vol) or the geometric-gap sampler
-# (MVTB_SPARSE_SP=1; fewer instructions but its per-thread scattered stores cost 15 us/vol on B200)
-SPARSE_SP = os.environ.get("MVTB_SPARSE_SP", "0") == "1"
+# in-kernel S&P sampler: the geometric-gap sampler (default; voxels hit are i.i.d. Bernoulli(p) with a fair
+# salt/pepper coin, exactly the reference's distribution, at a cost ~ p: 6.7 us/vol) or one Philox uniform per
+# voxel (MVTB_SPARSE_SP=0; bound by Philox's 32x32->64 multiplies: 7.9 us/vol)
+SPARSE_SP = os.environ.get("MVTB_SPARSE_SP", "1") == "1"
 BYTES_PER_VOXEL = 8            # algorithmic: read fp32 once + write fp32 once
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -343,8 +344,8 @@ def main():
         own = {"k_bl_fwd_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_h": 4 + 8.0 * nf / SHAPE[0],
                "k_rows_fwd": 8.0, "k_rows_inv": 8.0, "k_axis<FWD>": 8.0, "k_axis<MID>": 8.0, "k_axis<INV>": 8.0,
                "k_salt_pepper<philox>": 8.0 if cfg["p"] is None else 4.0 * cfg["p"]}.get(dom, 8.0)
-        # DRAM bytes per volume from the ncu --set full capture of this command (profiles/r01_ncu_full_selected_metrics.csv)
-        ncu_traffic = {"k_bl_fwd_h": 39.73e6, "k_bl_inv_h": 38.72e6, "k_salt_pepper<philox>": 23.86e6}.get(dom)
+        # DRAM bytes per volume from the ncu --set full capture of this command (profiles/r01_ncu_full_final_selected_metrics.csv)
+        ncu_traffic = {"k_bl_fwd_h": 39.44e6, "k_bl_inv_h": 38.72e6, "k_salt_pepper<philox>": 23.76e6 if SPARSE_SP else 23.85e6}.get(dom)
         alg_bytes = own * vox * units_per_launch
         achieved = alg_bytes / (kd["avg_launch_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -424,7 +425,7 @@ def main():
             "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % C, "samples_per_gpu": B,
                        "volumes_per_step_per_gpu": vols_per_step, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs larger than L2 (%.2f GB in + out per step per GPU)" % (2 * voxels * 4 / 1e9),
-                       "rng": "in-kernel Philox4x32-10, " + ("geometric-gap Bernoulli sampler (cost ~ p)" if SPARSE_SP else "one uniform per voxel")},
+                       "rng": "in-kernel Philox4x32-10, " + ("geometric-gap sampler: i.i.d. Bernoulli(p) hits + fair salt/pepper coin, cost ~ p" if SPARSE_SP else "one uniform per voxel")},
             "channel_volumes_per_s": value * C,
             "roofline": roofline,
             "roofline_whole_step": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

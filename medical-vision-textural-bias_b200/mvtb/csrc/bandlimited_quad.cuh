@@ -558,7 +558,10 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
 // memory for the D-axis DFT and the pointwise stage, and the same thread expands its column back and overwrites
 // Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
 template <int NF>
-__global__ void __launch_bounds__(160, 3)
+#ifndef MVTB_MIDW_MINB
+#define MVTB_MIDW_MINB 4
+#endif
+__global__ void __launch_bounds__(160, MVTB_MIDW_MINB)
 k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
     constexpr int NT = BlDims<NF>::NT, U = 8;
     MVTB_DYN_SMEM(smem_raw);

@@ -241,45 +241,75 @@ k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigne
 // (binary search, exact integer compares); one more random bit picks salt or pepper (the reference's
 // u <= p/2 | u <= p is a fair coin).  The voxels hit are i.i.d. Bernoulli(p), as with one uniform per voxel,
 // at a cost proportional to p.  Counter layout: (offset + global block id, call index, tag 0x5350).
+// Two phases per warp.  (1) Every lane walks its own block and only *lists* its hits in shared memory.  (2) The
+// warp writes the lists out block by block: one store instruction carries all hits of one 1 KB block.  Storing
+// from inside the walk (lane i at its own block, 32 blocks = 32 KB apart per instruction, a block's dozen hits
+// spread over the thread's lifetime) made every 4-byte read-modify-write of a sector its own DRAM page visit:
+// 1.6 TB/s, 15 us per volume, twice the dense kernel.
+static_assert(MVTB_SP_BLOCK == 256, "the hit lists pack the position into 8 bits");
+static const int kSpListCap = 40;        // hits listed per block; Poisson(256 p) rarely exceeds it, the rest is stored directly
+
 __global__ void __launch_bounds__(128)
 k_salt_pepper_sparse(float* __restrict__ x, size_t n_per_sample, unsigned blocks_per_sample,
-                     const unsigned* __restrict__ table, uint64_t seed, uint64_t offset, const float* __restrict__ mm) {
+                     const unsigned* __restrict__ table, float inv_log2q, uint64_t seed, uint64_t offset,
+                     const float* __restrict__ mm) {
     __shared__ unsigned sT[MVTB_SP_BLOCK];
+    __shared__ unsigned short sl[128][kSpListCap];    // position (8 bits) | coin << 8
+    __shared__ int sn[128];
     for (int e = threadIdx.x; e < MVTB_SP_BLOCK; e += blockDim.x) sT[e] = __ldg(table + e);
     __syncthreads();
     const unsigned smp = blockIdx.y;
     const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;       // block within the sample
-    if (b >= blocks_per_sample) return;
     const float lo = 0.5f * __ldg(mm + 2 * smp), hi = 0.5f * __ldg(mm + 2 * smp + 1);
+    const bool live = b < blocks_per_sample;
     const size_t j0 = (size_t)b * MVTB_SP_BLOCK;
-    const int len = (int)((n_per_sample - j0) < (size_t)MVTB_SP_BLOCK ? (n_per_sample - j0) : (size_t)MVTB_SP_BLOCK);
+    const int len = live ? (int)((n_per_sample - j0) < (size_t)MVTB_SP_BLOCK ? (n_per_sample - j0) : (size_t)MVTB_SP_BLOCK) : 0;
     float* xb = x + (size_t)smp * n_per_sample + j0;
     const uint64_t gb = offset + (uint64_t)smp * blocks_per_sample + b;
     uint2 key;
     key.x = (unsigned)seed;
     key.y = (unsigned)(seed >> 32);
-    int pos = -1;
-    for (unsigned call = 0;; ++call) {
+    int pos = -1, nlist = 0;
+    for (unsigned call = 0; live; ++call) {
         const uint4 r = Philox::run(make_uint4((unsigned)gb, (unsigned)(gb >> 32), call, 0x5350u), key);
         const unsigned words[2] = {r.x, r.y};
         bool done = false;
         MVTB_UNROLL
         for (int t = 0; t < 2; ++t) {
             const unsigned w = words[t];
-            // gap = smallest k with w < T[k]; T is non-decreasing; k = MVTB_SP_BLOCK means "beyond this block"
-            int lo_k = 0, hi_k = MVTB_SP_BLOCK;
-            MVTB_UNROLL
-            for (int step = 0; step < 9; ++step) {                  // 257 outcomes (0..MVTB_SP_BLOCK): 9 halvings
-                if (lo_k < hi_k) {
-                    const int mid = (lo_k + hi_k) >> 1;
-                    if (w < sT[mid]) hi_k = mid; else lo_k = mid + 1;
-                }
-            }
+            // gap = smallest k with w < T[k]; T is non-decreasing; k = MVTB_SP_BLOCK means "beyond this block".
+            // T[k] ~ 2^32 (1 - q^(k+1)), so k ~ floor(log2(1 - w / 2^32) / log2 q): one MUFU guess, then the exact
+            // integer table settles it (usually zero or one probe each way): the binary search's result, bit for bit.
+            const float v = (float)(~w) * 2.3283064365386963e-10f;          // 1 - w / 2^32 without cancellation
+#ifdef MVTB_EMU
+            const float kf = log2f(v) * inv_log2q;
+#else
+            const float kf = __log2f(v) * inv_log2q;
+#endif
+            int lo_k = (int)fminf(fmaxf(kf, 0.f), (float)MVTB_SP_BLOCK);    // NaN -> 0 (fmaxf) -> corrected below
+            while (lo_k > 0 && w < sT[lo_k - 1]) --lo_k;
+            while (lo_k < MVTB_SP_BLOCK && w >= sT[lo_k]) ++lo_k;
             pos += lo_k + 1;
-            if (!done && pos < len) xb[pos] = ((r.z >> t) & 1u) ? hi : lo;
-            else done = true;
+            if (!done && pos < len) {
+                const unsigned coin = (r.z >> t) & 1u;
+                if (nlist < kSpListCap) sl[threadIdx.x][nlist++] = (unsigned short)(pos | (coin << 8));
+                else xb[pos] = coin ? hi : lo;
+            } else {
+                done = true;
+            }
         }
         if (done) break;
+    }
+    sn[threadIdx.x] = nlist;
+    __syncwarp();
+    const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+    float* xw = x + (size_t)smp * n_per_sample + (size_t)(blockIdx.x * blockDim.x + w0) * MVTB_SP_BLOCK;
+    for (int j = 0; j < 32; ++j) {
+        const int nj = sn[w0 + j];
+        for (int i = lane; i < nj; i += 32) {
+            const unsigned e = sl[w0 + j][i];
+            xw[(size_t)j * MVTB_SP_BLOCK + (e & 255u)] = (e >> 8) ? hi : lo;
+        }
     }
 }
 
@@ -432,9 +462,12 @@ extern "C" int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_
     if (rc != MVTB_OK) return rc;
     // 1 KB table: a pageable async copy is staged by the runtime before this call returns
     MVTB_CUDA(cudaMemcpyAsync(table_dev, host_table, sizeof(host_table), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    if (p == 0.f) return MVTB_OK;                      // T = 0 everywhere: no voxel is ever selected
     const unsigned gx = (unsigned)((bps + 127) / 128);
+    const double l2q = log2(1.0 - (double)p);          // -inf for p = 1: the guess is then 0 and the table decides
+    const float inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
     MVTB_LAUNCH(k_salt_pepper_sparse, dim3(gx, (unsigned)n_samples), dim3(128), 0, stream, x, n_per_sample, (unsigned)bps,
-                (const unsigned*)table_dev, seed, offset, minmax);
+                (const unsigned*)table_dev, inv_log2q, seed, offset, minmax);
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;
 }
