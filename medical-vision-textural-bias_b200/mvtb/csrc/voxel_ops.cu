@@ -248,8 +248,10 @@ k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigne
 // 1.6 TB/s, 15 us per volume, twice the dense kernel.
 // kSpNB consecutive blocks per thread are walked in one flat loop (one Philox call per trip, whichever block the
 // thread is in), which keeps a warp converged longer; measured on B200 at p = 0.05: 6.7 us/volume with 1 block per
-// thread, 7.2 with 2, 7.5 with 4 -- the kernel is bound by the length of the per-thread dependent chain, so more,
-// shorter threads win over less divergence.
+// thread, 7.2 with 2, 7.5 with 4.  Evaluating four Philox calls (eight gaps) per trip with a branch-free table
+// lookup, so that their latencies overlap, changed nothing (6.7): at 3.6 TB/s of 32-byte sector read-modify-write
+// (the same 24 MB per volume the dense kernel moves at 3.0 TB/s) the kernel sits on the memory system's rate for
+// partial-sector writes, not on instructions.
 static_assert(MVTB_SP_BLOCK == 256, "the hit lists pack the position into 8 bits");
 static const int kSpNB = 1;              // consecutive blocks per thread
 static const int kSpListCap = 40;        // hits listed per thread (mean 12.8 per block at p = 0.05); the rest is stored directly
