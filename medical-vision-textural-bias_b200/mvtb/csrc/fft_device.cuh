@@ -78,14 +78,9 @@ struct Butterfly<5, INV> {
     }
 };
 
-// ---- exact division of small non-negative ints by a loop-invariant divisor: x / d = umulhi(x, M) when x d < 2^32
+// ---- exact division of small non-negative ints by a loop-invariant divisor: x / d = umulhi(x, M) when x d < 2^32,
+// M = floor(2^32 / d) + 1 (2^32 / d itself when d is a power of two), computed on the host (PassDev)
 struct FastDiv { int d; unsigned M; };
-__device__ __forceinline__ FastDiv fastdiv_make(int d) {
-    FastDiv f;
-    f.d = d;
-    f.M = d > 1 ? 0xFFFFFFFFu / (unsigned)d + 1u : 0u;     // floor(2^32 / d) + 1  (2^32 / d itself when d is a power of two)
-    return f;
-}
 __device__ __forceinline__ FastDiv fastdiv_from(int d, unsigned M) { FastDiv f; f.d = d; f.M = M; return f; }
 __device__ __forceinline__ int fastdiv(int x, const FastDiv& f) { return f.d > 1 ? (int)__umulhi((unsigned)x, f.M) : x; }
 

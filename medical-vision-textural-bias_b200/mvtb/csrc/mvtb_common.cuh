@@ -117,11 +117,6 @@ struct DescDev {
     int wrap_naxes;
     SpikeDev sp[MVTB_MAX_SPIKES];
 };
-#define MVTB_DESC_PACK 8
-struct DescPack {
-    int n;                       // 1 (shared) or number of volumes in this launch
-    DescDev d[MVTB_DESC_PACK];
-};
 
 }  // namespace mvtb
 
