@@ -238,10 +238,14 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-volumes", type=int, default=6, help="bounded CPU-baseline sample (volumes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--disk-r", type=float, default=None, help="override the disk radius (sweeps; the headline uses the workload's 12.5)")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
     if args.batch:
         cfg["batch"] = args.batch
+    if args.disk_r is not None:
+        cfg["r"] = args.disk_r
+        cfg["name"] += " [disk radius overridden: r=%g]" % args.disk_r
     args.warmup = max(args.warmup, 0)
 
     rank = int(os.environ.get("RANK", "0"))

@@ -722,7 +722,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
         }
         const size_t smem_mw = smem_w + sizeof(cf) * ((size_t)K * g.D + (size_t)K * K + g.D);
-        if (NF <= 16 && smem_mw <= 72 * 1024 && p->opt_fusemid) {
+        if (NF <= 26 && smem_mw <= 113 * 1024 && p->opt_fusemid) {       // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);
             auto kern = k_bl_midw<NF>;
@@ -797,8 +797,8 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
-    if (CPT == 2 && (rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
-    if (CPT == 2) MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if ((rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
+    MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MVTB_OK;
 }
 #endif

@@ -557,11 +557,10 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
 // Y[f_h][.][d] once (pair folding over w, 16 loads in flight), the 2F+1 W-bins of all columns meet in shared
 // memory for the D-axis DFT and the pointwise stage, and the same thread expands its column back and overwrites
 // Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
+// CTAs per SM: 4 up to NF = 16 (96 registers), 3 at NF = 20, 2 beyond (the 4 NF accumulator registers dominate)
+#define MVTB_MIDW_MINB(NF) ((NF) <= 16 ? 4 : ((NF) <= 20 ? 3 : 2))
 template <int NF>
-#ifndef MVTB_MIDW_MINB
-#define MVTB_MIDW_MINB 4
-#endif
-__global__ void __launch_bounds__(160, MVTB_MIDW_MINB)
+__global__ void __launch_bounds__(160, MVTB_MIDW_MINB(NF))
 k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
     constexpr int NT = BlDims<NF>::NT, U = 8;
     MVTB_DYN_SMEM(smem_raw);
