@@ -721,8 +721,9 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                             in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
             }
         }
-        const size_t smem_mw = smem_w + sizeof(cf) * ((size_t)K * g.D + (size_t)K * K + g.D);
-        if (NF <= 26 && smem_mw <= 113 * 1024 && p->opt_fusemid) {       // at least 2 CTAs per SM
+        const size_t bins = sizeof(cf) * (size_t)K * K;                      // shares the front of the buffer with the W table
+        const size_t smem_mw = ((smem_w > bins ? smem_w : bins) + 15) / 16 * 16 + sizeof(cf) * ((size_t)K * g.D + g.D);
+        if (smem_mw <= 113 * 1024 && p->opt_fusemid) {                      // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);
             auto kern = k_bl_midw<NF>;

@@ -565,10 +565,14 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     constexpr int NT = BlDims<NF>::NT, U = 8;
     MVTB_DYN_SMEM(smem_raw);
     const int W = g.W, D = g.D, F = g.F, K = 2 * F + 1;
+    // The W table is dead between the two W-axis phases, which is exactly when the [K][K] bins live: they share
+    // the front of the buffer and the table is reloaded (from L2) before the way back.
+    const size_t sc_bytes = sizeof(float) * (size_t)(W / 2 + 1) * NT, sb_bytes = sizeof(cf) * (size_t)K * K;
+    const size_t front = ((sc_bytes > sb_bytes ? sc_bytes : sb_bytes) + 15) / 16 * 16;
     float* sc = (float*)smem_raw;                        // (cos, sin) rows of the W axis, 0 .. W/2
-    cf* sg = (cf*)(sc + (W / 2 + 1) * NT);               // [K][D]  W-bins of every column
-    cf* sb = sg + K * D;                                 // [K][K]  bins after the pointwise stage
-    cf* st = sb + K * K;                                 // [D]     exp(-2 pi i t / D)
+    cf* sb = (cf*)smem_raw;                              // [K][K]  bins after the pointwise stage
+    cf* sg = (cf*)(smem_raw + front);                    // [K][D]  W-bins of every column
+    cf* st = sg + K * D;                                 // [D]     exp(-2 pi i t / D)
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int vol = blockIdx.x / NF, fh = blockIdx.x - vol * NF;
     bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);
@@ -678,6 +682,8 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
         const cf bp = sb[jw * K + F + fd], bm = sb[jw * K + F - fd];
         seo[o] = fd == 0 ? make_float4(bp.x, bp.y, 0.f, 0.f) : make_float4(bp.x + bm.x, bp.y + bm.y, bp.x - bm.x, bp.y - bm.y);
     }
+    __syncthreads();
+    bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);      // over the bins, which are no longer needed
     __syncthreads();
 
     // ---- back along D (into registers) and along W (streamed out in place)
