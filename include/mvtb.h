@@ -126,6 +126,12 @@ int mvtb_philox_uniform_f32(float* out, size_t n, uint64_t seed, uint64_t offset
  * (SURVEY A.3).  Returns MVTB_EUNSUPPORTED for an odd axis (use the chain). in != out. */
 int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W, int D, float alpha, void* stream);
 
+/* WrapArtifact.__call__ (F:503-515) on (H, W, D) volumes with even H and W and any D (BraTS: 240 x 240 x 155, where
+ * the odd D has no half shift): H and W are folded in the image domain, D is filtered row by row (forward FFT,
+ * parity weight, inverse FFT in one kernel).  16 B/voxel instead of the chain's five passes.  plan: a 3-D plan of
+ * that shape.  MVTB_EUNSUPPORTED for odd H or W (use the chain with wrap weights).  in != out. */
+int mvtb_wrap_odd_last_f32(mvtb_plan* plan, const float* in, float* out, int n_volumes, float alpha, void* stream);
+
 /* ---- measurement hooks (bench.py): per-kernel device time from cudaEvents recorded on the
  * launching stream around every launch a plan makes, and a process-wide launch counter. */
 #define MVTB_K_ROWS_FWD 0
@@ -140,6 +146,7 @@ int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W,
 #define MVTB_K_BL_INV_H 9
 #define MVTB_K_SPIKE_REDUCE 10
 #define MVTB_K_SPIKE_APPLY 11
+#define MVTB_K_ROWS_WRAP 12
 #define MVTB_K_KINDS 16
 int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
 /* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */

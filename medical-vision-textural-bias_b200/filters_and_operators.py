@@ -304,8 +304,9 @@ class SaltAndPepper(MapTransform, RandomizableTransform):
 class WrapArtifact(Transform):
     """Wraparound artifact: odd fftshift-ed k-space samples along H, W and D scaled by alpha (F:488-537).
 
-    Even H, W, D: exact image-domain fold (8 taps, one read + one write per voxel).  Otherwise the
-    k-space chain with the parity weights."""
+    Even H, W, D: exact image-domain fold (8 taps, one read + one write per voxel).  Even H, W and odd D
+    (240 x 240 x 155): folds along H and W plus a one-kernel FFT filter along D.  Otherwise the k-space chain with
+    the parity weights."""
 
     def __init__(self, alpha: float = 0.5):
         self.alpha = alpha
@@ -317,6 +318,8 @@ class WrapArtifact(Transform):
         x, src = Fn.to_device(img)
         if all(int(s) % 2 == 0 for s in x.shape[1:]):
             y = Fn.wrap_fold(x, float(self.alpha))
+        elif int(x.shape[1]) % 2 == 0 and int(x.shape[2]) % 2 == 0:
+            y = Fn.wrap_odd_last(x, float(self.alpha))
         else:
             y = Fn.kspace_chain(x, 3, [host.make_desc(wrap_alpha=float(self.alpha), wrap_naxes=3)])
         return Fn.back(y, src)

@@ -254,6 +254,88 @@ k_rows_inv(const cf* __restrict__ ws, float* __restrict__ out, AxisDev ax, int n
     if (uniform) block_minmax_commit(lo, hi, minmax + 2 * ((row_base + row_first) / rows_per_sample));
 }
 
+// ------------------------------------------------------------------ wraparound with an odd last axis (240 x 240 x 155)
+// WrapArtifact (F:503-515) weights the odd fftshift-ed k-space samples of every axis by alpha.  Along an even axis
+// that is an image-domain fold; along an odd axis there is no half shift, but the weight depends on
+// that axis' frequency alone, so it is a 1-D filter of every row: two real rows = one complex FFT, and because the
+// weight is symmetric under f -> -f it applies to the packed spectrum directly -- forward, weight, inverse in one
+// kernel, no unpacking.  k_wrap_fold_hw folds H and W first (the two commute).
+template <int MAXR>
+__global__ void __launch_bounds__(128, MVTB_MINB(MAXR))
+k_rows_wrap(const float* in, float* out, AxisDev ax, int pitch, int pairs_per_cta,
+            long long n_rows, float alpha) {
+    MVTB_DYN_SMEM(smem_raw);
+    cf* s = (cf*)smem_raw;
+    const int n = ax.n, tid = threadIdx.x, nthr = blockDim.x;
+    const long long n_pairs = (n_rows + 1) >> 1;
+    const long long pair0 = (long long)blockIdx.x * pairs_per_cta;
+    long long rem = n_pairs - pair0;
+    const int np = rem < pairs_per_cta ? (int)rem : pairs_per_cta;
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    for (int rp = wid; rp < np; rp += nw) {
+        const long long ra = 2 * (pair0 + rp);
+        const float* pa = in + ra * n;
+        const bool hasb = ra + 1 < n_rows;
+        cf* sr = s + rp * pitch;
+        for (int j = lane; j < n; j += 32) {
+            cp_async<4>(&sr[j].x, pa + j);
+            if (hasb) cp_async<4>(&sr[j].y, pa + n + j);
+            else sr[j].y = 0.f;
+        }
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    cf* scratch = ax.generic ? s + (size_t)pairs_per_cta * pitch : nullptr;
+    fft_forward<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, scratch);
+    const float inv_n = 1.f / (float)n;
+    for (int j = lane; j < n; j += 32) {
+        const int i = (__ldg(ax.pos2k + j) + n / 2) % n;             // fftshift-ed index of the bin at position j
+        const float wgt = (i & 1) ? alpha * inv_n : inv_n;
+        for (int rp = wid; rp < np; rp += nw) {
+            cf* e = s + rp * pitch + j;
+            *e = cscale(*e, wgt);
+        }
+    }
+    __syncthreads();
+    fft_inverse<false, MAXR>(ax, s, pitch, 1, np, tid, nthr, scratch);
+    for (int rp = wid; rp < np; rp += nw) {
+        const long long ra = 2 * (pair0 + rp);
+        const bool hasb = ra + 1 < n_rows;
+        const cf* sr = s + rp * pitch;
+        float* pa = out + ra * n;
+        for (int j = lane; j < n; j += 32) {
+            const cf z = sr[j];
+            pa[j] = z.x;
+            if (hasb) pa[n + j] = z.y;
+        }
+    }
+}
+
+// H and W folds of one orbit {h, h+H/2} x {w, w+W/2} at every d: 4 reads, 4 writes, d contiguous across threads
+__global__ void __launch_bounds__(256)
+k_wrap_fold_hw(const float* __restrict__ in, float* __restrict__ out, int H, int W, int D, float c0, float ch, float cw,
+               size_t n_total) {
+    const int H2 = H / 2, W2 = W / 2;
+    const size_t per_vol = (size_t)H2 * W2 * D, vol_elems = (size_t)H * W * D;
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t v = t / per_vol;
+        size_t r = t - v * per_vol;
+        const int d = (int)(r % D); r /= D;
+        const int w = (int)(r % W2);
+        const int h = (int)(r / W2);
+        const float* x = in + v * vol_elems;
+        float* y = out + v * vol_elems;
+        const size_t o00 = ((size_t)h * W + w) * D + d, o01 = o00 + (size_t)W2 * D;
+        const size_t o10 = o00 + (size_t)H2 * W * D, o11 = o10 + (size_t)W2 * D;
+        const float a00 = x[o00], a01 = x[o01], a10 = x[o10], a11 = x[o11];
+        const float b00 = c0 * a00 + cw * a01, b01 = c0 * a01 + cw * a00;     // W axis
+        const float b10 = c0 * a10 + cw * a11, b11 = c0 * a11 + cw * a10;
+        y[o00] = c0 * b00 + ch * b10; y[o10] = c0 * b10 + ch * b00;           // H axis
+        y[o01] = c0 * b01 + ch * b11; y[o11] = c0 * b11 + ch * b01;
+    }
+}
+
 // ------------------------------------------------------------------ pointwise k-space stage
 __device__ __forceinline__ long long mask_term(int kind, int i, int n) {
     const long long d = kind == MVTB_MASK_DISK ? (long long)(i - n / 2) : (long long)(2 * i - (n - 1));
@@ -449,6 +531,7 @@ static int configure_maxr(int optin) {
     int rc;
     if ((rc = allow_big_smem(k_rows_fwd<MAXR>, optin)) != MVTB_OK) return rc;
     if ((rc = allow_big_smem(k_rows_inv<MAXR>, optin)) != MVTB_OK) return rc;
+    if ((rc = allow_big_smem(k_rows_wrap<MAXR>, optin)) != MVTB_OK) return rc;
     if ((rc = allow_big_smem(k_axis<AX_FWD, MAXR>, optin)) != MVTB_OK) return rc;
     if ((rc = allow_big_smem(k_axis<AX_INV, MAXR>, optin)) != MVTB_OK) return rc;
     if ((rc = allow_big_smem(k_axis<AX_MID, MAXR>, optin)) != MVTB_OK) return rc;
@@ -704,6 +787,40 @@ extern "C" int mvtb_kspace_logabs_sum_f32(mvtb_plan* p, const float* in, int n_v
         }
         rc = launch_axis<AX_STATS>(p, p->ws, mid, nv, g, nullptr, 1, sums_out + v0, stream);
         if (rc != MVTB_OK) return rc;
+    }
+    MVTB_CUDA(cudaGetLastError());
+    return MVTB_OK;
+}
+
+extern "C" int mvtb_wrap_odd_last_f32(mvtb_plan* p, const float* in, float* out, int n_volumes, float alpha, void* stream) {
+    if (!p || !in || !out) { set_error("wrap_odd_last: null argument"); return MVTB_EINVAL; }
+    if (n_volumes < 0) { set_error("wrap_odd_last: n_volumes=%d", n_volumes); return MVTB_EINVAL; }
+    if (in == out) { set_error("wrap_odd_last: in-place is not supported"); return MVTB_EINVAL; }
+    if (p->ndim != 3 || p->lead_drop != 0 || (p->shape[1] & 1) || (p->shape[2] & 1)) {
+        set_error("wrap_odd_last: needs a 3-D plan with even H and W (use the k-space chain)");
+        return MVTB_EUNSUPPORTED;
+    }
+    if (n_volumes == 0) return MVTB_OK;
+    MVTB_CUDA(cudaSetDevice(p->device));
+    const int D = p->shape[0], W = p->shape[1], H = p->shape[2];
+    const float c0 = 0.5f * (1.f + alpha), c1 = 0.5f * (1.f - alpha);
+    const float ch = ((H / 2) & 1) ? -c1 : c1, cw = ((W / 2) & 1) ? -c1 : c1;
+    const size_t orbits = (size_t)n_volumes * (H / 2) * (W / 2) * D;
+    size_t blocks = (orbits + 255) / 256;
+    if (blocks > (size_t)148 * 32) blocks = (size_t)148 * 32;
+    MVTB_LAUNCH(k_wrap_fold_hw, dim3((unsigned)blocks), dim3(256), 0, stream, in, out, H, W, D, c0, ch, cw, orbits);
+    const long long n_rows = (long long)n_volumes * H * W;
+    const long long n_pairs = (n_rows + 1) / 2;
+    const int rp = p->rows_pairs_per_cta;
+    const unsigned grid = (unsigned)((n_pairs + rp - 1) / rp);
+    const size_t smem = (size_t)rp * p->row_pitch * sizeof(cf) * (p->ax[0].generic ? 2 : 1);
+    {
+        ProfScope prof(p, MVTB_K_ROWS_WRAP, stream);
+        switch (axis_maxr(p, 0)) {
+            case 5: { auto kern = k_rows_wrap<5>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, (const float*)out, out, p->ax[0], p->row_pitch, rp, n_rows, alpha); break; }
+            case 13: { auto kern = k_rows_wrap<13>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, (const float*)out, out, p->ax[0], p->row_pitch, rp, n_rows, alpha); break; }
+            default: { auto kern = k_rows_wrap<31>; MVTB_LAUNCH(kern, dim3(grid), dim3(kThreads), smem, stream, (const float*)out, out, p->ax[0], p->row_pitch, rp, n_rows, alpha); break; }
+        }
     }
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;

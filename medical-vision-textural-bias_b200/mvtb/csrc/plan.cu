@@ -363,7 +363,7 @@ extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load()
 
 extern "C" const char* mvtb_kernel_name(int kind) {
     static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
-                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "", "", "", ""};
+                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "k_rows_wrap", "", "", ""};
     return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
 }
 

@@ -194,6 +194,22 @@ def wrap_fold(x: torch.Tensor, alpha: float) -> torch.Tensor:
     return y
 
 
+def wrap_odd_last(x: torch.Tensor, alpha: float) -> torch.Tensor:
+    """Wraparound on (..., H, W, D) with even H, W and any D: image-domain folds along H and W, a one-kernel
+    FFT filter along D (mvtb_wrap_odd_last_f32); raises MvtbError(EUNSUPPORTED) for odd H or W."""
+    L = _lib.lib()
+    shp = tuple(int(s) for s in x.shape[-3:])
+    nvol = x.numel() // (shp[0] * shp[1] * shp[2]) if x.numel() else 0
+    y = torch.empty_like(x)
+    if nvol == 0:
+        return y
+    plan = get_plan(shp, nvol, x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_wrap_odd_last_f32(plan, _ptr(x), _ptr(y), nvol, C.c_float(alpha), _stream(x.device))
+    _lib.check(L, rc)
+    return y
+
+
 # ----------------------------------------------------------------------------- batched chain-127 convenience
 def chain127(x: torch.Tensor, *, r: float, spike_idx: Optional[Sequence[Sequence[int]]], intensity: float,
              alpha: Optional[float], p: Optional[float], u: Optional[torch.Tensor] = None, seed: int = 0,

@@ -220,6 +220,25 @@ def test_emu_wrap_fold(name):
     assert rel_l2(y, z["y"]) <= TOL
 
 
+@pytest.mark.parametrize("name", [n for n in golden_names("wrap_") if "s9x15x25" not in n])
+def test_emu_wrap_odd_last(name):
+    """Even H and W, any D (incl. 31, 155 and the even ones): folds along H, W + one-kernel FFT filter along D."""
+    m, z = load_golden(name)
+    x = np.ascontiguousarray(z["x"])
+    y = np.empty_like(x)
+    L = emu.lib()
+    plan = emu.Plan(x.shape[1:], 2)
+    B.check(L, L.mvtb_wrap_odd_last_f32(plan.h, emu.ptr(x), emu.ptr(y), x.shape[0], C.c_float(m["alpha"]), None))
+    assert rel_l2(y, z["y"]) <= TOL
+
+
+def test_emu_wrap_odd_last_rejects_odd_h_or_w():
+    x = np.zeros((1, 9, 15, 25), dtype=np.float32)
+    L = emu.lib()
+    plan = emu.Plan(x.shape[1:], 1)
+    assert L.mvtb_wrap_odd_last_f32(plan.h, emu.ptr(x), emu.ptr(np.empty_like(x)), 1, C.c_float(0.5), None) == B.MVTB_EUNSUPPORTED
+
+
 def test_emu_wrap_fold_rejects_odd_axis():
     x = np.zeros((1, 4, 6, 5), dtype=np.float32)
     L = emu.lib()

@@ -69,3 +69,24 @@ def test_arbitrary_axis_lengths_prime_factors_above_31(cuda_device, shape):
     assert rel_l2(y.numpy(), P.gibbs_noise(x, 0.4).numpy()) <= TOL
     yd = F.RandFourierDiskMaskd("image", r=12.5, prob=1.)({"image": x.to(cuda_device)})["image"].cpu()
     assert rel_l2(yd.numpy(), P.fourier_disk_mask(x, 12.5, False).numpy()) <= TOL
+
+
+@pytest.mark.parametrize("shape,alpha", [((2, 240, 240, 155), 0.5), ((1, 240, 240, 155), 0.0), ((3, 64, 48, 31), 0.25)])
+def test_wrap_odd_last_axis_dedicated_path(cuda_device, shape, alpha):
+    """WrapArtifact on BraTS-shaped volumes (even H, W, odd D): the folds + one-kernel D filter, not the 5-pass chain."""
+    import ctypes as C
+    import filters_and_operators as F
+    from mvtb import _lib, functional as Fn
+    from oracle import ref_port as P
+    x = P.synthetic_volume(70, shape)
+    plan = Fn.get_plan(shape[1:], shape[0], cuda_device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    y = F.WrapArtifact(alpha)(x.to(cuda_device))
+    torch.cuda.synchronize()
+    ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
+    assert kinds == {"k_rows_wrap"}
+    assert rel_l2(y.cpu().numpy(), P.wrap_artifact(x, alpha).numpy()) <= TOL
