@@ -96,17 +96,29 @@ struct StageTask {
         cf v[R];
         MVTB_UNROLL
         for (int q = 0; q < R; ++q) v[q] = p[q * es];
+        // w^q, q = 1..R-1, from one table load and R-2 complex products: the table loads go through the same LSU
+        // pipe as the tile traffic, which is the busiest unit of these kernels; the FMA pipe has room
         if (INV) {
             if (j != 0) {
+                const cf w1 = __ldg(tw + j * tstep);
+                cf wq = w1;
                 MVTB_UNROLL
-                for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * tstep));
+                for (int q = 1; q < R; ++q) {
+                    v[q] = cmulc(v[q], wq);
+                    if (q + 1 < R) wq = cmul(wq, w1);
+                }
             }
             Butterfly<R, true>::run(v, tw, 0);
         } else {
             Butterfly<R, false>::run(v, tw, 0);
             if (j != 0) {
+                const cf w1 = __ldg(tw + j * tstep);
+                cf wq = w1;
                 MVTB_UNROLL
-                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], __ldg(tw + j * q * tstep));
+                for (int q = 1; q < R; ++q) {
+                    v[q] = cmul(v[q], wq);
+                    if (q + 1 < R) wq = cmul(wq, w1);
+                }
             }
         }
         MVTB_UNROLL
@@ -206,36 +218,54 @@ __device__ __forceinline__ void fft_task2(cf* p, int e1, int e2, int m2, int j2,
                 MVTB_UNROLL
                 for (int a = 0; a < R1; ++a) t[a] = v[a][c];
                 Butterfly<R1, false>::run(t, tw, 0);
-                const int j1 = (c * m2 + j2) * ts1;
+                const cf w1 = __ldg(tw + (c * m2 + j2) * ts1);
+                cf wa = w1;
                 MVTB_UNROLL
-                for (int a = 1; a < R1; ++a) t[a] = cmul(t[a], __ldg(tw + j1 * a));
+                for (int a = 1; a < R1; ++a) {
+                    t[a] = cmul(t[a], wa);
+                    if (a + 1 < R1) wa = cmul(wa, w1);
+                }
                 MVTB_UNROLL
                 for (int a = 0; a < R1; ++a) v[a][c] = t[a];
             }
+            cf w2[R2];                                      // stage 2 twiddles w_m1^(j2 c): the same for every a
+            w2[0] = cmk(1.f, 0.f);
+            w2[1] = __ldg(tw + j2 * ts2);
             MVTB_UNROLL
-            for (int a = 0; a < R1; ++a) {                  // stage 2: over p2, twiddle w_m1^(j2 q2)
+            for (int c = 2; c < R2; ++c) w2[c] = cmul(w2[c - 1], w2[1]);
+            MVTB_UNROLL
+            for (int a = 0; a < R1; ++a) {                  // stage 2: over p2
                 Butterfly<R2, false>::run(v[a], tw, 0);
                 if (j2 != 0) {
                     MVTB_UNROLL
-                    for (int c = 1; c < R2; ++c) v[a][c] = cmul(v[a][c], __ldg(tw + j2 * c * ts2));
+                    for (int c = 1; c < R2; ++c) v[a][c] = cmul(v[a][c], w2[c]);
                 }
             }
         } else {
+            cf w2[R2];
+            w2[0] = cmk(1.f, 0.f);
+            w2[1] = __ldg(tw + j2 * ts2);
+            MVTB_UNROLL
+            for (int c = 2; c < R2; ++c) w2[c] = cmul(w2[c - 1], w2[1]);
             MVTB_UNROLL
             for (int a = 0; a < R1; ++a) {
                 if (j2 != 0) {
                     MVTB_UNROLL
-                    for (int c = 1; c < R2; ++c) v[a][c] = cmulc(v[a][c], __ldg(tw + j2 * c * ts2));
+                    for (int c = 1; c < R2; ++c) v[a][c] = cmulc(v[a][c], w2[c]);
                 }
                 Butterfly<R2, true>::run(v[a], tw, 0);
             }
             MVTB_UNROLL
             for (int c = 0; c < R2; ++c) {
                 cf t[R1];
-                const int j1 = (c * m2 + j2) * ts1;
+                const cf w1 = __ldg(tw + (c * m2 + j2) * ts1);
+                cf wa = w1;
                 t[0] = v[0][c];
                 MVTB_UNROLL
-                for (int a = 1; a < R1; ++a) t[a] = cmulc(v[a][c], __ldg(tw + j1 * a));
+                for (int a = 1; a < R1; ++a) {
+                    t[a] = cmulc(v[a][c], wa);
+                    if (a + 1 < R1) wa = cmul(wa, w1);
+                }
                 Butterfly<R1, true>::run(t, tw, 0);
                 MVTB_UNROLL
                 for (int a = 0; a < R1; ++a) v[a][c] = t[a];
