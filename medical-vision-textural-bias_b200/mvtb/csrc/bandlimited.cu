@@ -1,19 +1,21 @@
 // bandlimited.cu — the k-space chain when the mask keeps only a small ball of frequencies.
 //
-// RandFourierDiskMaskd (F:236-252) with the radii the scripts use (r = 9 ... 15; r = 12.5 in the
+// RandFourierDiskMaskd (F:236-252) with the radii the scripts use (r = 9 ... 30; r = 12.5 in the
 // 125/126/127 chains) keeps |f_d| <= F = floor(sqrt(thr)) on every axis, i.e. (2F+1)^2 (F+1) of the
 // N_h N_w N_d/2 half-spectrum bins (8 125 of 4.5 M for 240x240x155, r = 12.5).  A full FFT computes
 // 550x more bins than survive the mask.  This path computes only the surviving ones, as pruned
-// DFTs with the symmetric-pair folding  x[h] +- x[N-h]  (cos part / sin part), in five kernels:
+// DFTs with the symmetric-pair folding  x[h] +- x[N-h]  (cos part / sin part), in three kernels:
 //
-//   k_bl_fwd_h   x[v][H][W*D] real       -> Y[v][NF][W*D]      thread = 2 (w,d) columns; streams the
-//                                                             volume ONCE from HBM with coalesced loads
-//   k_bl_fwd_w   Y[v][NF][W][D]          -> G[v][NF][K][D]     K = 2F+1
-//   k_bl_mid     G: D-axis DFT to K bins, pointwise (mask / in-box spikes / wrap / 1/N), back
-//   k_bl_inv_w   G[v][NF][K][D]          -> Y[v][NF][W][D]
-//   k_bl_inv_h   Y                       -> out[v][H][W*D]     thread = 2 columns, writes the volume
-//                                                             ONCE; adds out-of-box spikes as plane waves
-//                                                              and tracks per-sample min/max
+//   k_bl_fwd_h   x[v][H][W*D] real       -> Y[v][NF][W*D]      streams the volume ONCE from HBM with coalesced
+//                                                             loads (cp.async ring); H % 4 == 0: four rows per
+//                                                             table row (bandlimited_quad.cuh)
+//   k_bl_midw    Y[v][NF][W][D] in place: one CTA per (v, f_h) plane does the W-axis DFT to K = 2F+1 bins, the
+//                D-axis DFT, the pointwise stage (mask / in-box spikes / wrap / 1/N) and both ways back
+//   k_bl_inv_h   Y                       -> out[v][H][W*D]     writes the volume ONCE; adds out-of-box spikes as
+//                                                             plane waves, tracks per-sample min/max
+//
+// (k_bl_fwd_w -> G[v][NF][K][D], k_bl_mid, k_bl_inv_w are the same W/D stage as three kernels: used when a plane's
+// tile would leave fewer than two CTAs per SM, and by tests through MVTB_PATH_BL_SPLIT.)
 //
 // HBM traffic is the compulsory 8 B/voxel plus ~1 B/voxel of intermediates (Y is NF/H of the
 // volume); arithmetic is ~(2F+1) FMA per voxel and direction.  cos/sin rows are read from shared

@@ -14,6 +14,8 @@
 //   k_axis<MID>           outermost axis: forward, pointwise (mask / spike / wrap / 1/N), inverse
 //   k_axis<INV>           middle axes back
 //   k_rows_inv            half-spectrum rows -> real rows, fused per-sample min/max
+// CTAs are 128 threads, 4-6 per SM; tiles arrive by cp.async; every per-pass constant comes from the plan (PassDev).
+// Also here: k_wrap_fold_hw + k_rows_wrap, the wraparound for volumes with even H, W and an odd last axis.
 #include <math.h>
 #include <string.h>
 

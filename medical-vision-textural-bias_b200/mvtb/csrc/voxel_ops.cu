@@ -1,5 +1,6 @@
 // voxel_ops.cu — HBM-bound voxel kernels: per-sample min/max, salt-and-pepper select with
-// injected uniforms or in-kernel Philox4x32-10, and the even-axis wraparound fold.
+// injected uniforms or in-kernel Philox4x32-10 (one uniform per voxel, or the geometric-gap sampler
+// whose cost is proportional to p), and the even-axis wraparound fold.
 //   SaltAndPepper.salt_and_pepper   F:465-482   (F = source_code/filters_and_operators.py)
 //   WrapArtifact.__call__           F:503-515   (image-domain form)
 #include <math.h>
