@@ -578,14 +578,24 @@ static int pick_nf(int need) {
 bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, int* F_out) {
     if (p->ndim != 3 || p->opt_path == MVTB_PATH_GENERAL || !p->bl_tab) return false;
     const long long thr = desc[0].mask_thresh;
+    const int kind = desc[0].mask_kind;
+    if (kind != MVTB_MASK_DISK && kind != MVTB_MASK_CENTRED) return false;
     for (int i = 0; i < n_desc; ++i) {
         const mvtb_chain_desc& d = desc[i];
-        if (d.mask_kind != MVTB_MASK_DISK || d.mask_ndim != 3 || d.inside_off || d.mask_thresh < 0) return false;
+        if (d.mask_kind != kind || d.mask_ndim != 3 || d.inside_off || d.mask_thresh < 0) return false;
         if (d.mask_thresh != thr) return false;
         if (d.wrap_naxes != 0 && d.wrap_naxes != 3) return false;
         if (d.n_spikes < 0 || d.n_spikes > MVTB_MAX_SPIKES) return false;
     }
-    const int F = isqrt_ll(thr);
+    // Largest |f| any kept bin (or its mirror, for M_eff) can have on one axis.  Disk: f^2 <= thr.  Centred masks
+    // (GibbsNoise, GibbsNoiseLayer) measure from (N-1)/2: the per-axis term is (2f+1)^2 on an even axis, (2f)^2 on
+    // an odd one, so |f| <= floor((s+1)/2) resp. floor(s/2) with s = floor(sqrt(thr)).  The pointwise stage applies
+    // the exact mask; this only sizes the box of frequencies that are computed at all.
+    int F = isqrt_ll(thr);
+    if (kind == MVTB_MASK_CENTRED) {
+        const bool any_even = !(p->shape[0] & 1) || !(p->shape[1] & 1) || !(p->shape[2] & 1);
+        F = any_even ? (F + 1) / 2 : F / 2;
+    }
     const int nf = pick_nf(F + 1);
     if (nf == 0) return false;
     if (2 * nf - 1 > p->shape[2] || 2 * F + 1 > p->shape[1] || 2 * F + 1 > p->shape[0]) return false;

@@ -139,3 +139,17 @@ def test_bl_many_volumes_chunked_workspace():
     yg, _, mg = run(x, descs, True, chunk=1, vps=4)
     assert rel_l2(yb, yg) <= TOL
     assert np.allclose(mb, mg, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("shape,alpha", [((2, 16, 12, 8), 0.8), ((1, 15, 12, 9), 0.7), ((1, 9, 15, 7), 0.75), ((3, 20, 18, 15), 0.9)])
+def test_bl_centred_masks_gibbs_noise(shape, alpha, fused):
+    """GibbsNoise / GibbsNoiseLayer masks (centre (N-1)/2, M_eff in {0, 1/2, 1} on even axes) with a small radius
+    take the band-limited path too: same numbers as the general path and the oracle."""
+    xt = P.synthetic_volume(7, shape)
+    x = xt.numpy()
+    d = host.make_desc(mask_kind=B.MASK_CENTRED, mask_ndim=3, mask_thresh=host.gibbs_threshold(alpha, shape[1:]))
+    yb, nb, _ = run(x, [d], general=False)
+    yg, ng, _ = run(x, [d], general=True)
+    ref = P.gibbs_noise(xt, alpha).numpy()
+    assert nb == (3 if fused else 5) and ng == 5      # 3 launches: only the band-limited path has that few
+    assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL

@@ -130,3 +130,24 @@ def test_spike_fast_path_matches_general_and_is_taken(cuda_device):
     for c in range(2):
         ref = P.plane_wave_spike(x[c:c + 1], idx[c], 15.0)
         assert rel_l2(y[c:c + 1].cpu().numpy(), ref.numpy()) <= TOL
+
+
+@pytest.mark.parametrize("shape,alpha", [((1, 240, 240, 155), 0.9), ((2, 128, 128, 64), 0.8), ((1, 240, 240, 155), 0.85)])
+def test_bl_centred_mask_gibbs_noise_small_radius(cuda_device, shape, alpha):
+    """GibbsNoise with alpha near 1 keeps a small centred ball: band-limited kernels, same numbers as the oracle."""
+    import ctypes as C
+    import filters_and_operators as F
+    from mvtb import _lib, functional as Fn
+    from oracle import ref_port as P
+    x = P.synthetic_volume(12, shape)
+    plan = Fn.get_plan(shape[1:], shape[0], cuda_device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    y = F.GibbsNoise(alpha)(x.to(cuda_device))
+    torch.cuda.synchronize()
+    ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
+    assert "k_bl_fwd_h" in kinds and "k_rows_fwd" not in kinds
+    assert rel_l2(y.cpu().numpy(), P.gibbs_noise(x, alpha).numpy()) <= TOL
