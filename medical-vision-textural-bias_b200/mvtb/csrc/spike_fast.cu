@@ -21,7 +21,9 @@ namespace mvtb {
 int plan_stage_upload(mvtb_plan* p, const void* src, size_t bytes, void* stream, void** dptr);   // plan.cu
 
 static const int kSpThreads = 256;
-static const int kSpRowsPerCta = 64;       // rows of the last axis per CTA (8 warps x 8 rows)
+static const int kSpGroupRows = 64;        // rows per pass over the CTA's span (8 warps x kSpUnroll rows)
+static const int kSpRowsPerCta = 256;      // rows of the last axis per CTA: four passes share one table load and setup
+                                           // (64 rows per CTA = 40 KB of volume per 5 KB table load: 15.6 us reduce, 19.2 us apply)
 
 struct SpVol {
     int n;
@@ -90,7 +92,7 @@ __device__ __forceinline__ cf sp_row_phase(const cf* st_s, const SpGeom& g, unsi
 // Per CTA: kSpRowsPerCta consecutive rows = one contiguous span of the volume, walked as a flat array with
 // kSpUnroll independent coalesced loads in flight per thread; the phase of each row's outer axes is
 // precomputed once per CTA in shared memory.
-static const int kSpUnroll = 8;
+static const int kSpUnroll = 8;            // 16 rows per warp and step is slower (26.7 vs 18.9 us per volume in k_spike_apply)
 
 __device__ __forceinline__ void sp_row_phases(cf* srow, const cf* st, const SpVol& sv, const SpGeom& g,
                                               long long row0, int nrows, int tid, int nthr) {
@@ -120,29 +122,31 @@ k_spike_reduce(const float* __restrict__ x, cf* __restrict__ partial, SpGeom g, 
     cf acc[MVTB_MAX_SPIKES];
     MVTB_UNROLL
     for (int s = 0; s < MVTB_MAX_SPIKES; ++s) acc[s] = cmk(0.f, 0.f);
-    // warp w owns rows 8w .. 8w+7 of the CTA's span: 8 independent coalesced loads per lane and step
+    // per pass, warp w owns kSpUnroll consecutive rows of a kSpGroupRows-row group: that many independent coalesced loads per lane and step
     const float* xb = x + ((size_t)vol * g.rows + row0) * n0;
-    const int rbase = wp * kSpUnroll;
-    const float* xr[kSpUnroll];                                  // rows past the end alias the last row; their
-    MVTB_UNROLL                                                  // row phase is 0, so they contribute nothing
-    for (int k = 0; k < kSpUnroll; ++k) xr[k] = xb + (size_t)(rbase + k < nrows ? rbase + k : nrows - 1) * n0;
-    for (int s = 0; s < sv.n; ++s) {
-        cf part[kSpUnroll];
-        MVTB_UNROLL
-        for (int k = 0; k < kSpUnroll; ++k) part[k] = cmk(0.f, 0.f);
-        for (int i = lane; i < n0; i += 32) {
-            float v[kSpUnroll];
+    for (int grp = 0; grp < kSpRowsPerCta && grp < nrows; grp += kSpGroupRows) {
+        const int rbase = grp + wp * kSpUnroll;
+        const float* xr[kSpUnroll];                              // rows past the end alias the last row; their
+        MVTB_UNROLL                                              // row phase is 0, so they contribute nothing
+        for (int k = 0; k < kSpUnroll; ++k) xr[k] = xb + (size_t)(rbase + k < nrows ? rbase + k : nrows - 1) * n0;
+        for (int s = 0; s < sv.n; ++s) {
+            cf part[kSpUnroll];
             MVTB_UNROLL
-            for (int k = 0; k < kSpUnroll; ++k) v[k] = xr[k][i];        // 8 unconditional loads in flight
-            const cf t = st[s * g.tlen + i];
+            for (int k = 0; k < kSpUnroll; ++k) part[k] = cmk(0.f, 0.f);
+            for (int i = lane; i < n0; i += 32) {
+                float v[kSpUnroll];
+                MVTB_UNROLL
+                for (int k = 0; k < kSpUnroll; ++k) v[k] = xr[k][i];    // kSpUnroll unconditional loads in flight
+                const cf t = st[s * g.tlen + i];
+                MVTB_UNROLL
+                for (int k = 0; k < kSpUnroll; ++k) { part[k].x = fmaf(v[k], t.x, part[k].x); part[k].y = fmaf(v[k], t.y, part[k].y); }
+            }
+            cf a_ = cmk(0.f, 0.f);
             MVTB_UNROLL
-            for (int k = 0; k < kSpUnroll; ++k) { part[k].x = fmaf(v[k], t.x, part[k].x); part[k].y = fmaf(v[k], t.y, part[k].y); }
+            for (int k = 0; k < kSpUnroll; ++k) a_ = cadd(a_, cmul(part[k], srow[s * kSpRowsPerCta + rbase + k]));
+            MVTB_UNROLL
+            for (int s2 = 0; s2 < MVTB_MAX_SPIKES; ++s2) if (s2 == s) acc[s2] = cadd(acc[s2], a_);
         }
-        cf a_ = cmk(0.f, 0.f);
-        MVTB_UNROLL
-        for (int k = 0; k < kSpUnroll; ++k) a_ = cadd(a_, cmul(part[k], srow[s * kSpRowsPerCta + rbase + k]));
-        MVTB_UNROLL
-        for (int s2 = 0; s2 < MVTB_MAX_SPIKES; ++s2) if (s2 == s) acc[s2] = a_;
     }
     MVTB_UNROLL
     for (int s = 0; s < MVTB_MAX_SPIKES; ++s) {
@@ -228,28 +232,30 @@ k_spike_apply(const float* __restrict__ x, float* __restrict__ out, const cf* __
     const float* xb = x + ((size_t)vol * g.rows + row0) * n0;
     float* ob = out + ((size_t)vol * g.rows + row0) * n0;
     float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
-    const int rbase = wp * kSpUnroll;
-    const float* xr[kSpUnroll];
-    MVTB_UNROLL
-    for (int k = 0; k < kSpUnroll; ++k) xr[k] = xb + (size_t)(rbase + k < nrows ? rbase + k : nrows - 1) * n0;
-    for (int i = lane; i < n0; i += 32) {
-        float v[kSpUnroll];
+    for (int grp = 0; grp < kSpRowsPerCta && grp < nrows; grp += kSpGroupRows) {
+        const int rbase = grp + wp * kSpUnroll;
+        const float* xr[kSpUnroll];
         MVTB_UNROLL
-        for (int k = 0; k < kSpUnroll; ++k) v[k] = xr[k][i];            // 8 unconditional loads in flight
-        for (int s = 0; s < sv.n; ++s) {
-            const cf t = st[s * g.tlen + i];
+        for (int k = 0; k < kSpUnroll; ++k) xr[k] = xb + (size_t)(rbase + k < nrows ? rbase + k : nrows - 1) * n0;
+        for (int i = lane; i < n0; i += 32) {
+            float v[kSpUnroll];
+            MVTB_UNROLL
+            for (int k = 0; k < kSpUnroll; ++k) v[k] = xr[k][i];        // kSpUnroll unconditional loads in flight
+            for (int s = 0; s < sv.n; ++s) {
+                const cf t = st[s * g.tlen + i];
+                MVTB_UNROLL
+                for (int k = 0; k < kSpUnroll; ++k) {
+                    const cf de = srow[s * kSpRowsPerCta + rbase + k];  // Delta_s * row phase (broadcast)
+                    v[k] += de.x * t.x - de.y * t.y;
+                }
+            }
             MVTB_UNROLL
             for (int k = 0; k < kSpUnroll; ++k) {
-                const cf de = srow[s * kSpRowsPerCta + rbase + k];      // Delta_s * row phase (broadcast)
-                v[k] += de.x * t.x - de.y * t.y;
-            }
-        }
-        MVTB_UNROLL
-        for (int k = 0; k < kSpUnroll; ++k) {
-            if (rbase + k < nrows) {
-                ob[(size_t)(rbase + k) * n0 + i] = v[k];
-                lo = fminf(lo, v[k]);
-                hi = fmaxf(hi, v[k]);
+                if (rbase + k < nrows) {
+                    ob[(size_t)(rbase + k) * n0 + i] = v[k];
+                    lo = fminf(lo, v[k]);
+                    hi = fmaxf(hi, v[k]);
+                }
             }
         }
     }
@@ -276,7 +282,7 @@ bool spike_fast_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_
     if (p->opt_path == MVTB_PATH_GENERAL) return false;
     long long tlen = 0, rows = 1;
     for (int a = 0; a < p->ndim; ++a) { tlen += p->shape[a]; if (a >= 1) rows *= p->shape[a]; }
-    if (sizeof(cf) * MVTB_MAX_SPIKES * (size_t)(tlen + 64) > 200 * 1024 || rows > 0x7fffffffLL) return false;   // tables must fit shared memory
+    if (sizeof(cf) * MVTB_MAX_SPIKES * (size_t)(tlen + kSpRowsPerCta) > 200 * 1024 || rows > 0x7fffffffLL) return false;   // tables must fit shared memory
     int total = 0;
     for (int i = 0; i < n_desc; ++i) {
         const mvtb_chain_desc& d = desc[i];
