@@ -504,11 +504,14 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
     else             { src0 = xv + (long long)(H2 + 1) * g.NC;    step = g.NC; }
     src0 += c0 + 4 * j;
     float* dst0 = ring + r * 256 + 4 * j;
+    const smem_addr_t dst_base = smem_addr(dst0);       // converted once; the loop does 32-bit slot arithmetic
     const int nq = H4 - 1;
     for (int q = 1; q < S; ++q) {                       // quads 1 .. S-1 in flight before the loop
-        if (q <= nq && piece_ok) cp_async16(dst0 + ((q - 1) % S) * 1024, src0 + (long long)(q - 1) * step);
+        if (q <= nq && piece_ok) cp_async16_at(dst_base + (q - 1) * 4096, src0 + (long long)(q - 1) * step);
         cp_async_commit();
     }
+    const float* src_next = src0 + (long long)(S - 1) * step;   // row of quad q - 1 + S, advanced every iteration
+    int slot = 0;                                               // (q - 1) % S
     bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
 
     const long long col = c0 + tid;
@@ -531,11 +534,14 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
         cp_async_wait<S - 2>();                         // this thread's piece of quad q has landed
         __syncthreads();                                // ... everyone's has, and stage(q-1) is no longer being read
         {
-            const int qn = q - 1 + S;                   // refill the stage read in the previous iteration
-            if (qn <= nq && piece_ok) cp_async16(dst0 + ((qn - 1) % S) * 1024, src0 + (long long)(qn - 1) * step);
+            // refill the stage read in the previous iteration: quad q - 1 + S goes to slot (q - 2) mod S
+            const int prev = slot == 0 ? S - 1 : slot - 1;
+            if (q - 1 + S <= nq && piece_ok) cp_async16_at(dst_base + prev * 4096, src_next);
             cp_async_commit();
+            src_next += step;
         }
-        const float* st = ring + ((q - 1) % S) * 1024 + tid;
+        const float* st = ring + slot * 1024 + tid;
+        slot = slot + 1 == S ? 0 : slot + 1;
         const float a = st[0], b = st[256], c = st[512], d = st[768];
         float2 cs[NF];
         bl_row<NF>(sc + q * NT, cs);

@@ -64,6 +64,18 @@ __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
 #endif
 }
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) { cp_async<16>(smem_dst, gsrc); }
+// the same with the shared-memory address converted once by the caller (32-bit arithmetic in the loop)
+#ifdef MVTB_EMU
+typedef unsigned char* smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(void* p) { return (unsigned char*)p; }
+__device__ __forceinline__ void cp_async16_at(smem_addr_t d, const void* gsrc) { cp_async<16>(d, gsrc); }
+#else
+typedef unsigned smem_addr_t;
+__device__ __forceinline__ smem_addr_t smem_addr(void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_at(smem_addr_t d, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+#endif
 __device__ __forceinline__ void cp_async_commit() {
 #ifndef MVTB_EMU
     asm volatile("cp.async.commit_group;" ::: "memory");
