@@ -264,3 +264,22 @@ def test_hostmem_cpulist_and_no_gpu_is_graceful():
     if not torch.cuda.is_available():
         assert hostmem.gpu_numa_node(0) is None
         assert hostmem.bind_to_gpu_numa_node(0)["bound"] is False
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) prints one JSON line with the contract keys."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "volumes/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("volumes/sec") and line["value"] > 0 and line["n_gpus"] == 1
+    assert line["config"]["workload"].startswith("cfg2")
+    assert line["e2e"] == {"value": line["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
