@@ -90,3 +90,27 @@ def test_wrap_odd_last_axis_dedicated_path(cuda_device, shape, alpha):
     kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
     assert kinds == {"k_rows_wrap"}
     assert rel_l2(y.cpu().numpy(), P.wrap_artifact(x, alpha).numpy()) <= TOL
+
+
+def test_cfg4_full_size_spike_property(cuda_device):
+    """BASELINE cfg 4 at its full size, (8192, 240, 240): after KSpaceSpikeNoise(loc, I) the bin at loc has magnitude
+    e^I and the phase it had, and nothing else in k-space moved (checked with torch.fft on a sample of slices)."""
+    import math
+    import filters_and_operators as F
+    g = torch.Generator(device=cuda_device).manual_seed(4)
+    x = torch.randn(8192, 240, 240, generator=g, device=cuda_device)
+    loc, inten = (120 + 31, 120 - 17), 9.0
+    y = F.KSpaceSpikeNoise(loc, inten)(x)
+    assert y.shape == x.shape and y.is_cuda
+    pick = torch.tensor([0, 1, 17, 4095, 4096, 8000, 8191], device=cuda_device)
+    kx = torch.fft.fftshift(torch.fft.fftn(x[pick].double(), dim=(-2, -1)), dim=(-2, -1))
+    ky = torch.fft.fftshift(torch.fft.fftn(y[pick].double(), dim=(-2, -1)), dim=(-2, -1))
+    a, b = loc
+    a2, b2 = (240 - a) % 240, (240 - b) % 240                  # the conjugate partner of a real image
+    want = math.exp(inten) * kx[:, a, b] / kx[:, a, b].abs()
+    got = 2 * ky[:, a, b] - kx[:, a, b]                          # taking the real part halves the change at each partner
+    assert torch.allclose(got, want, rtol=2e-4, atol=0)
+    d = (ky - kx)
+    d[:, a, b] = 0
+    d[:, a2, b2] = 0
+    assert float(d.abs().pow(2).sum().sqrt() / kx.abs().pow(2).sum().sqrt()) <= 1e-5
