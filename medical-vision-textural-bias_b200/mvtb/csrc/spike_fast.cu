@@ -237,10 +237,14 @@ k_spike_apply(const float* __restrict__ x, float* __restrict__ out, const cf* __
         const float* xr[kSpUnroll];
         MVTB_UNROLL
         for (int k = 0; k < kSpUnroll; ++k) xr[k] = xb + (size_t)(rbase + k < nrows ? rbase + k : nrows - 1) * n0;
+        float v[kSpUnroll], vn[kSpUnroll];
+        MVTB_UNROLL
+        for (int k = 0; k < kSpUnroll; ++k) v[k] = lane < n0 ? xr[k][lane] : 0.f;
         for (int i = lane; i < n0; i += 32) {
-            float v[kSpUnroll];
+            // software pipeline: the loads of the next 32 columns are in flight while this step computes and stores
+            const int inext = i + 32;
             MVTB_UNROLL
-            for (int k = 0; k < kSpUnroll; ++k) v[k] = xr[k][i];        // kSpUnroll unconditional loads in flight
+            for (int k = 0; k < kSpUnroll; ++k) vn[k] = inext < n0 ? xr[k][inext] : 0.f;
             for (int s = 0; s < sv.n; ++s) {
                 const cf t = st[s * g.tlen + i];
                 MVTB_UNROLL
@@ -257,6 +261,8 @@ k_spike_apply(const float* __restrict__ x, float* __restrict__ out, const cf* __
                     hi = fmaxf(hi, v[k]);
                 }
             }
+            MVTB_UNROLL
+            for (int k = 0; k < kSpUnroll; ++k) v[k] = vn[k];
         }
     }
     if (minmax != nullptr) {
