@@ -368,38 +368,15 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     const bool col_ok = i0 + t < inner;
     const long long gstep = (long long)(nthr >> lgT) * inner;
 
-    {   // the whole tile in flight at once: 8-byte asynchronous copies, no registers held
-        const cf* gp = base + (long long)(tid >> lgT) * inner + t;
-        if (col_ok) {
-            for (int e = tid; e < n * T; e += nthr, gp += gstep) cp_async<8>(s + e, gp);
-        } else {
-            for (int e = tid; e < n * T; e += nthr) s[e] = cmk(0.f, 0.f);
-        }
-        cp_async_commit();
-    }
-
-    cf* scratch = ax.generic ? s + (size_t)n * T : nullptr;
-
-    // ---- pointwise stage, part 1 (while the tile is still in flight): what depends only on the bin along this
-    // axis goes into a shared table, what depends only on the column into registers.
-    int4* tab = nullptr;                   // per position j: (shifted index, mask term at +f, mask term at -f, odd)
+    // ---- pointwise stage, what depends only on the column (registers), computed before anything is loaded: a tile
+    // whose columns the mask removes entirely (all bins of the column and of its mirror lie outside the ball, no
+    // spike on it) is zero whatever the data, so it is neither loaded nor transformed -- 40 % of the tiles for
+    // GibbsNoise(0.5) on 240 x 240 x 155, 85 % for a disk of radius 40.
     long long qp = 0, qn = 0;
     float wgt = g.scale;
     unsigned mpos = 0, mneg = 0;           // per-spike "all lower axes match" bits
     if (MODE == AX_MID) {
         const DescDev& d = dv[dshared ? 0 : (int)o];
-        tab = (int4*)(smem_raw + (((size_t)n * T * sizeof(cf) * (ax.generic ? 2 : 1)) + 15) / 16 * 16);
-        const bool masked = d.mask_kind != MVTB_MASK_NONE && axis < d.mask_ndim;
-        for (int j = tid; j < n; j += nthr) {
-            const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
-            const int imn = (2 * (n / 2) - im + n) % n;
-            int4 e;
-            e.x = im;
-            e.y = masked ? (int)mask_term(d.mask_kind, im, n) : 0;      // < (2n)^2 <= 2^30 for any tile that fits
-            e.z = masked ? (int)mask_term(d.mask_kind, imn, n) : 0;
-            e.w = (axis < d.wrap_naxes && (im & 1)) ? 1 : 0;
-            tab[j] = e;
-        }
         int ish[MVTB_MAX_FFT_DIMS], ineg[MVTB_MAX_FFT_DIMS];
         long long rest = i0 + t;
         {
@@ -429,6 +406,55 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             }
             mpos |= (pm ? 1u : 0u) << sI;
             mneg |= (qm ? 1u : 0u) << sI;
+        }
+        bool col_dead = !col_ok;
+        if (col_ok && d.mask_kind != MVTB_MASK_NONE && !d.inside_off && (mpos | mneg) == 0u) {
+            // smallest term this axis can add: 0, or 1 for a centred mask on an even axis ((2i - (n-1))^2 is odd)
+            const long long tmin = (axis < d.mask_ndim && d.mask_kind != MVTB_MASK_DISK && !(n & 1)) ? 1 : 0;
+            col_dead = qp + tmin > d.thr && qn + tmin > d.thr;
+        }
+        __shared__ int s_alive;
+        if (tid == 0) s_alive = 0;
+        __syncthreads();
+        if (!col_dead) s_alive = 1;
+        __syncthreads();
+        if (!s_alive) {
+            if (col_ok) {
+                cf* gz = base + (long long)(tid >> lgT) * inner + t;
+                for (int e = tid; e < n * T; e += nthr, gz += gstep) *gz = cmk(0.f, 0.f);
+            }
+            return;
+        }
+    }
+
+    {   // the whole tile in flight at once: 8-byte asynchronous copies, no registers held
+        const cf* gp = base + (long long)(tid >> lgT) * inner + t;
+        if (col_ok) {
+            for (int e = tid; e < n * T; e += nthr, gp += gstep) cp_async<8>(s + e, gp);
+        } else {
+            for (int e = tid; e < n * T; e += nthr) s[e] = cmk(0.f, 0.f);
+        }
+        cp_async_commit();
+    }
+
+    cf* scratch = ax.generic ? s + (size_t)n * T : nullptr;
+
+    // ---- pointwise stage, part 1 (while the tile is still in flight): what depends only on the bin along this
+    // axis goes into a shared table, what depends only on the column into registers.
+    int4* tab = nullptr;                   // per position j: (shifted index, mask term at +f, mask term at -f, odd)
+    if (MODE == AX_MID) {
+        const DescDev& d = dv[dshared ? 0 : (int)o];
+        tab = (int4*)(smem_raw + (((size_t)n * T * sizeof(cf) * (ax.generic ? 2 : 1)) + 15) / 16 * 16);
+        const bool masked = d.mask_kind != MVTB_MASK_NONE && axis < d.mask_ndim;
+        for (int j = tid; j < n; j += nthr) {
+            const int im = (__ldg(ax.pos2k + j) + n / 2) % n;
+            const int imn = (2 * (n / 2) - im + n) % n;
+            int4 e;
+            e.x = im;
+            e.y = masked ? (int)mask_term(d.mask_kind, im, n) : 0;      // < (2n)^2 <= 2^30 for any tile that fits
+            e.z = masked ? (int)mask_term(d.mask_kind, imn, n) : 0;
+            e.w = (axis < d.wrap_naxes && (im & 1)) ? 1 : 0;
+            tab[j] = e;
         }
     }
     cp_async_wait<0>();
