@@ -153,3 +153,22 @@ def test_bl_centred_masks_gibbs_noise(shape, alpha, fused):
     ref = P.gibbs_noise(xt, alpha).numpy()
     assert nb == (3 if fused else 5) and ng == 5      # 3 launches: only the band-limited path has that few
     assert rel_l2(yb, ref) <= TOL and rel_l2(yg, ref) <= TOL
+
+
+@pytest.mark.parametrize("spike_d", [None, 38])
+def test_general_path_skips_tiles_the_mask_removes(spike_d):
+    """General FFT path with a small ball on a long last axis (D = 40: half-spectrum bins 16..20 form a tile that the
+    mask removes whatever the other frequencies are): the skipped tiles must come out as exact zeros in k-space,
+    i.e. the result still equals the band-limited path and the oracle -- also when a spike sits in such a tile."""
+    shape = (3, 8, 6, 40)
+    xt = P.synthetic_volume(13, shape)
+    x = xt.numpy()
+    thr = host.disk_threshold(3.2, shape[1:])
+    sp = [((4 + 1, 3, spike_d), host.exp_f32(5.0))] if spike_d is not None else []
+    d = disk(thr, spikes=sp)
+    yg, _, _ = run(x, [d], general=True)
+    yb, _, _ = run(x, [d], general=False)
+    assert rel_l2(yg, yb) <= TOL
+    if spike_d is None:
+        ref = torch.stack([P.fourier_disk_mask(xt[c], 3.2) for c in range(3)]).numpy()
+        assert rel_l2(yg, ref) <= TOL
