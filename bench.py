@@ -38,6 +38,9 @@ SHAPE = (240, 240, 155)
 # salt/pepper coin, exactly the reference's distribution, at a cost ~ p: 6.7 us/vol) or one Philox uniform per
 # voxel (MVTB_SPARSE_SP=0; bound by Philox's 32x32->64 multiplies: 7.9 us/vol)
 SPARSE_SP = os.environ.get("MVTB_SPARSE_SP", "1") == "1"
+# chain and select pass as ONE library call: on the band-limited path the select runs inside the persistent inverse
+# kernel, on output lines still in L2 (MVTB_TWO_CALLS=1: the round-1 sequence of two calls, same result bit for bit)
+FUSED_SP = os.environ.get("MVTB_TWO_CALLS", "0") != "1"
 BYTES_PER_VOXEL = 8            # algorithmic: read fp32 once + write fp32 once
 FALLBACK_HBM_GBS = 6650.0      # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
@@ -218,11 +221,14 @@ def gpu_step(cfg, x, idxs, out, step, group_offset=None):
         descs.extend([d] * C)
     if cfg["p"] is None:
         return Fn.kspace_chain(x, 3, descs, out=out)
-    y, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C, out=out)
     if SPARSE_SP:                                   # geometric-gap Bernoulli sampler: counters count 256-voxel blocks
         nb = B * ((x.numel() // B + 255) // 256)
         off = step * nb if group_offset is None else group_offset // 64
+        if FUSED_SP:                                # chain + select as one library call (mvtb_kspace_chain_sp_f32)
+            return Fn.kspace_chain_sp(x, 3, descs, cfg["p"], seed=2024, offset=off, vols_per_sample=C, out=out)[0]
+        y, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C, out=out)
         return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=off, n_samples=B, mm=mm, out=y, sparse=True)
+    y, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C, out=out)
     n4 = (x.numel() + 3) // 4
     off = step * n4 if group_offset is None else group_offset
     return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=off, n_samples=B, mm=mm, out=y)
@@ -238,6 +244,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-volumes", type=int, default=6, help="bounded CPU-baseline sample (volumes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel sweeps)")
     ap.add_argument("--disk-r", type=float, default=None, help="override the disk radius (sweeps; the headline uses the workload's 12.5)")
     args = ap.parse_args()
     cfg = dict(WORKLOADS[args.workload])
@@ -319,7 +326,7 @@ def main():
         if cnts[k]:
             kernels[L.mvtb_kernel_name(k).decode()] = {"launches_per_step": cnts[k] / prof_steps, "ms_per_step": ms_sum[k] / prof_steps,
                                                        "avg_launch_ms": ms_sum[k] / cnts[k]}
-    if cfg["p"] is not None:                          # the select pass is launched from Python: time it the same way
+    if cfg["p"] is not None and not (FUSED_SP and SPARSE_SP):   # a separate select pass is launched from Python: time it the same way
         from mvtb import functional as Fn2
         mm = Fn2.minmax(out, B)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -345,7 +352,7 @@ def main():
         # between the kernel that reads the volume once and the one that writes it once; the intermediates
         # they exchange are NF/H of a volume.  The whole-step figure below uses the full 8 B/voxel.
         nf = 13
-        own = {"k_bl_fwd_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_h": 4 + 8.0 * nf / SHAPE[0],
+        own = {"k_bl_fwd_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_sp": 4 + 8.0 * nf / SHAPE[0],
                "k_rows_fwd": 8.0, "k_rows_inv": 8.0, "k_axis<FWD>": 8.0, "k_axis<MID>": 8.0, "k_axis<INV>": 8.0,
                "k_salt_pepper<philox>": 8.0 if cfg["p"] is None else 4.0 * cfg["p"]}.get(dom, 8.0)
         # DRAM bytes per volume from the ncu --set full capture of this command (profiles/r01_ncu_full_final_selected_metrics.csv)
@@ -364,7 +371,9 @@ def main():
     # ---- end to end through the public API with host buffers: every step copies the batch from pinned host
     # memory, runs the chain, and copies the result back.  The batch moves in slices so that the H2D copy of
     # slice i+1, the kernels of slice i and the D2H copy of slice i-1 overlap (three streams, PCIe is duplex).
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 20))
+    if args.no_e2e:
+        e2e_steps = 0
     from mvtb import hostmem
     affinity0 = os.sched_getaffinity(0)
     numa = hostmem.bind_to_gpu_numa_node(local_rank)           # pinned pages are first-touched on the GPU's node
@@ -398,18 +407,20 @@ def main():
                 ev_out[i].record(s_out)
         main.wait_stream(s_out)
 
-    e2e_step(0)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for s in range(e2e_steps):
-        e2e_step(s + 1)
-    t1.record()
-    barrier()
-    e2e_ms = t0.elapsed_time(t1)
-    e2e_checksum = float(hy.double().sum())
+    e2e_ms, e2e_checksum = float("nan"), None
+    if e2e_steps:
+        e2e_step(0)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0.record()
+        for s in range(e2e_steps):
+            e2e_step(s + 1)
+        t1.record()
+        barrier()
+        e2e_ms = t0.elapsed_time(t1)
+        e2e_checksum = float(hy.double().sum())
     os.sched_setaffinity(0, affinity0)
 
     # ---- max over ranks, whole-job aggregate; NCCL only gathers statistics
@@ -420,7 +431,7 @@ def main():
 
     if rank == 0:
         value = total_vols_per_step * args.steps / (ms * 1e-3)
-        e2e_value = total_vols_per_step * e2e_steps / (e2e_ms * 1e-3)
+        e2e_value = total_vols_per_step * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
         step_bytes = BYTES_PER_VOXEL * voxels
         line = {
             "metric": "volumes/sec (240x240x155 fp32)", "value": value, "unit": "volumes/s", "n_gpus": world,

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MVTB_VERSION 100
+#define MVTB_VERSION 200
 
 #define MVTB_OK 0
 #define MVTB_EINVAL (-1)        /* bad argument (null pointer, non-positive size, ...) */
@@ -89,6 +89,16 @@ int mvtb_kspace_chain_f32(mvtb_plan* plan, const float* in, float* out, int n_vo
                           const mvtb_chain_desc* desc, int n_desc,
                           float* minmax_out, int vols_per_sample, void* stream);
 
+/* mvtb_kspace_chain_f32 followed by mvtb_salt_pepper_sparse_f32(out, vols_per_sample * volume, n_volumes /
+ * vols_per_sample samples, seed, offset, p, minmax_out): the whole 127-series chain (F:236-252 -> F:370-393 ->
+ * F:503-515 -> F:465-482) in one call, with bit-identical results to the two calls.  When the mask keeps a small
+ * ball (band-limited path) the select pass runs inside the inverse kernel, on output lines that are still in L2,
+ * instead of as a second pass over HBM.  minmax_out (required): device float[2 * n_samples].  n_volumes must be a
+ * multiple of vols_per_sample.  in == out is allowed. */
+int mvtb_kspace_chain_sp_f32(mvtb_plan* plan, const float* in, float* out, int n_volumes,
+                             const mvtb_chain_desc* desc, int n_desc, float* minmax_out, int vols_per_sample,
+                             float p, uint64_t seed, uint64_t offset, void* stream);
+
 /* sum over the full (unshifted, unnormalised) spectrum of log(|k| + 1e-10) per volume, into
  * device double[n_volumes]; the caller divides by the volume size and multiplies by 2.5
  * (KSpaceSpikeNoise default intensity F:932-933, RandKSpaceSpikeNoise default range F:1127-1130). */
@@ -147,6 +157,7 @@ int mvtb_wrap_odd_last_f32(mvtb_plan* plan, const float* in, float* out, int n_v
 #define MVTB_K_SPIKE_REDUCE 10
 #define MVTB_K_SPIKE_APPLY 11
 #define MVTB_K_ROWS_WRAP 12
+#define MVTB_K_BL_INV_SP 13
 #define MVTB_K_KINDS 16
 int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
 /* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */

@@ -46,6 +46,8 @@ _SYMBOLS = {
     "mvtb_plan_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "mvtb_kspace_chain_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ChainDesc), C.c_int,
                                         C.c_void_p, C.c_int, C.c_void_p]),
+    "mvtb_kspace_chain_sp_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ChainDesc), C.c_int,
+                                           C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]),
     "mvtb_kspace_logabs_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_minmax_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_salt_pepper_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,

@@ -25,8 +25,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
+#include "philox.cuh"
 #include "pointwise.cuh"
 
 namespace mvtb {
@@ -556,6 +558,7 @@ k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cb
 }
 
 #include "bandlimited_quad.cuh"
+#include "bandlimited_sp.cuh"
 
 // ------------------------------------------------------------------ host side
 size_t bl_workspace_per_volume(const mvtb_plan* p, int F);
@@ -645,9 +648,33 @@ static int bl_make_vol(const mvtb_plan* p, const BlGeom& g, const mvtb_chain_des
     return convert_desc(p, &inbox, &out->d);
 }
 
+// One period of the fused kernel's work queue (bandlimited_sp.cuh): the A inverse tiles of a sample at times
+// 0 .. A-1, merged with the B select tiles of earlier samples at times lag + spread * j / B after their own sample's
+// first inverse tile came A earlier (wrapped into the period, `periods back` recorded per entry).
+static void is_build_pattern(int A, int B, int lag, int spread, std::vector<unsigned>& pat, int* max_back) {
+    struct Ent { double t; unsigned e; };
+    std::vector<Ent> v;
+    v.reserve((size_t)A + B);
+    for (int j = 0; j < A; ++j) v.push_back(Ent{(double)j, (unsigned)j});
+    int mb = 0;
+    for (int j = 0; j < B; ++j) {
+        const double tau = (double)lag + (double)spread * (double)j / (double)B;
+        int back = 1 + (int)floor(tau / (double)A);
+        if (back > 7) back = 7;
+        double tin = tau - (double)(back - 1) * A;
+        if (tin > (double)A) tin = (double)A;
+        if (back > mb) mb = back;
+        v.push_back(Ent{tin + 0.5, MVTB_IS_SELECT | ((unsigned)back << 28) | (unsigned)j});
+    }
+    std::stable_sort(v.begin(), v.end(), [](const Ent& x, const Ent& y) { return x.t < y.t; });
+    pat.resize(v.size());
+    for (size_t i = 0; i < v.size(); ++i) pat[i] = v[i].e;
+    *max_back = mb;
+}
+
 template <int NF>
 static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
-                  int F, float* minmax_out, int vols_per_sample, void* stream) {
+                  int F, float* minmax_out, int vols_per_sample, void* stream, SpFuse* sp) {
     BlGeom g;
     g.D = p->shape[0]; g.W = p->shape[1]; g.H = p->shape[2];
     g.F = F;
@@ -682,18 +709,74 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 tw[(size_t)jd * g.D + d].y = (float)sin(ang);
             }
     }
-    void* dvp = nullptr;
-    int rc = plan_stage_upload(p, hbuf.data(), hbuf.size(), stream, &dvp);
-    if (rc != MVTB_OK) return rc;
-    const BlVol* dv = (const BlVol*)dvp;
-    const cf* dtw = (const cf*)((const unsigned char*)dvp + vol_bytes);
     const int shared_desc = n_desc == 1 ? 1 : 0;
     const bool quad = (g.H % 4) == 0 && p->opt_quad;      // four rows per table row (bandlimited_quad.cuh)
+    constexpr int CPT = BlCols<NF>::CPT;
 
     // intermediates are ~NF/H of a volume each: keep up to kBlChunk volumes in flight so that the small
     // W-axis / mid kernels get enough CTAs to fill the machine
     const size_t per_vol = bl_workspace_per_volume(p, F);
     int chunk = n_volumes < kBlChunk ? n_volumes : kBlChunk;
+
+    // ---- fused inverse + salt-and-pepper (bandlimited_sp.cuh): when the two-column quad kernel applies
+    const int vps = vols_per_sample;
+    bool fuse = sp != nullptr && p->opt_fusesp && sp->p > 0.f && minmax_out != nullptr && quad && CPT == 2 && (g.NC % 2) == 0 &&
+                g.NC * (long long)g.H < 0x7fffffffLL && (((uintptr_t)out) & 7) == 0 && g.H / 4 - 1 >= 1 &&
+                vps >= 1 && vps <= kBlChunk && n_volumes % vps == 0;
+    IsArgs ia;
+    memset(&ia, 0, sizeof(ia));
+    std::vector<unsigned> pattern;
+    int max_back = 0;
+    size_t pat_off = 0, tab_off = 0;
+    if (fuse) {
+        if (p->is_chunk > 0 && p->is_chunk < chunk) chunk = p->is_chunk;
+        chunk -= chunk % vps;                             // whole samples per launch
+        int HS = p->is_hs;
+        if (HS > g.H / 4 - 1) HS = g.H / 4 - 1;
+        if (HS < 1) HS = 1;
+        ia.HS = HS;
+        ia.vps = vps;
+        ia.ncb2 = (int)((g.NC / 2 + kColThreads - 1) / kColThreads);
+        ia.A = vps * ia.ncb2 * HS;
+        ia.n_per_sample = (unsigned long long)vps * p->vol_real;
+        const unsigned long long bps = (ia.n_per_sample + MVTB_SP_BLOCK - 1) / MVTB_SP_BLOCK;
+        const unsigned long long B = (bps + 255) / 256;
+        if (bps > 0x7fffffffull || B >= (1ull << 28) || (unsigned long long)ia.A >= (1ull << 28)) fuse = false;
+        else {
+            ia.bps = (unsigned)bps;
+            const int lag = p->is_lag >= 0 ? p->is_lag : 2 * p->num_sms + 8;
+            const int spread = (int)((long long)ia.A * p->is_spread_pct / 100);
+            is_build_pattern(ia.A, (int)B, lag, spread, pattern, &max_back);
+            ia.period = (int)pattern.size();
+            ia.list_cap = sp->p <= 0.08f ? 40 : (sp->p <= 0.16f ? 64 : 112);
+            const double l2q = log2(1.0 - (double)sp->p);
+            ia.inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
+            ia.seed = sp->seed;
+            ia.offset = sp->offset;
+            ia.minmax = minmax_out;
+        }
+    }
+    if (fuse) {
+        pat_off = hbuf.size();
+        hbuf.resize(pat_off + sizeof(unsigned) * pattern.size());
+        memcpy(hbuf.data() + pat_off, pattern.data(), sizeof(unsigned) * pattern.size());
+        tab_off = hbuf.size();
+        hbuf.resize(tab_off + sizeof(unsigned) * MVTB_SP_BLOCK);
+        int rct = mvtb_sparse_table(sp->p, (unsigned*)(hbuf.data() + tab_off));
+        if (rct != MVTB_OK) return rct;
+    }
+    void* dvp = nullptr;
+    int rc = plan_stage_upload(p, hbuf.data(), hbuf.size(), stream, &dvp);
+    if (rc != MVTB_OK) return rc;
+    const BlVol* dv = (const BlVol*)dvp;
+    const cf* dtw = (const cf*)((const unsigned char*)dvp + vol_bytes);
+    if (fuse) {
+        ia.pattern = (const unsigned*)((const unsigned char*)dvp + pat_off);
+        ia.table = (const unsigned*)((const unsigned char*)dvp + tab_off);
+        const size_t need = sizeof(unsigned) * (size_t)(1 + kBlChunk);
+        if (!p->is_sync) MVTB_CUDA(cudaMalloc((void**)&p->is_sync, need));
+        ia.sync = p->is_sync;
+    }
     if (p->bl_ws_bytes < per_vol * (size_t)chunk) {
         if (p->bl_ws) cudaFree(p->bl_ws);                // synchronises with work that may still use it
         p->bl_ws = nullptr;
@@ -701,7 +784,6 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         MVTB_CUDA(cudaMalloc((void**)&p->bl_ws, per_vol * (size_t)chunk));
         p->bl_ws_bytes = per_vol * (size_t)chunk;
     }
-    constexpr int CPT = BlCols<NF>::CPT;
     const int cols_per_cta = kColThreads * CPT;
     const int n_cblocks = (int)((g.NC + cols_per_cta - 1) / cols_per_cta);
     const int n_tblocks = (NF * g.D + kWThreads - 1) / kWThreads;
@@ -756,7 +838,21 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)G, Y, g, n_tblocks);
             }
         }
-        {
+        if (fuse) {
+            ProfScope prof(p, MVTB_K_BL_INV_SP, stream);
+            ia.nsamp = nv / vps;
+            ia.s_base = v0 / vps;
+            ia.total = (unsigned)((ia.nsamp + max_back) * ia.period);
+            MVTB_CUDA(cudaMemsetAsync(ia.sync, 0, sizeof(unsigned) * (size_t)(1 + ia.nsamp), (cudaStream_t)stream));
+            const size_t smem_is = smem_hi + sizeof(unsigned) * MVTB_SP_BLOCK + sizeof(int) * 256 +
+                                   sizeof(unsigned short) * 256 * (size_t)ia.list_cap;
+            unsigned grid = (unsigned)(p->num_sms * 2);
+            if (grid > ia.total) grid = ia.total;
+            float* o = out + (size_t)v0 * p->vol_real;
+            if (p->is_store == 0) { auto kern = k_bl_inv_sp<NF, 0>; MVTB_LAUNCH(kern, dim3(grid), dim3(256), smem_is, stream, (const cf*)Y, o, g, dv, v0, shared_desc, ia); }
+            else if (p->is_store == 2) { auto kern = k_bl_inv_sp<NF, 2>; MVTB_LAUNCH(kern, dim3(grid), dim3(256), smem_is, stream, (const cf*)Y, o, g, dv, v0, shared_desc, ia); }
+            else { auto kern = k_bl_inv_sp<NF, 1>; MVTB_LAUNCH(kern, dim3(grid), dim3(256), smem_is, stream, (const cf*)Y, o, g, dv, v0, shared_desc, ia); }
+        } else {
             ProfScope prof(p, MVTB_K_BL_INV_H, stream);
             if (quad && CPT == 2 && (g.NC % 2) == 0 && g.NC * (long long)g.H < 0x7fffffffLL && (((uintptr_t)out) & 7) == 0) {
                 const int ncb2 = (int)((g.NC / 2 + kColThreads - 1) / kColThreads);
@@ -773,19 +869,21 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
     }
     MVTB_CUDA(cudaGetLastError());
+    if (sp) sp->done = fuse;
     return MVTB_OK;
 }
 
 int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
-             int F, float* minmax_out, int vols_per_sample, void* stream) {
+             int F, float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse) {
+    SpFuse* sp = (SpFuse*)sp_fuse;
     switch (pick_nf(F + 1)) {
-        case 4: return bl_run<4>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 8: return bl_run<8>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 13: return bl_run<13>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 16: return bl_run<16>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 20: return bl_run<20>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 26: return bl_run<26>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
-        case 32: return bl_run<32>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream);
+        case 4: return bl_run<4>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 8: return bl_run<8>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 13: return bl_run<13>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 16: return bl_run<16>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 20: return bl_run<20>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 26: return bl_run<26>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 32: return bl_run<32>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
         default: set_error("band-limited path: F=%d not instantiated", F); return MVTB_EUNSUPPORTED;
     }
 }
@@ -810,6 +908,9 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 0>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 1>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 2>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
     MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MVTB_OK;

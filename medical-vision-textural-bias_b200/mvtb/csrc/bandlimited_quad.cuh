@@ -306,72 +306,70 @@ __device__ __forceinline__ void bl_unit32(int f, int n, int N, float* c, float* 
     sincospif(2.0f * (float)m / (float)N, s, c);
 }
 
+// How the output rows leave: 0 = streaming (evict-first: the volume is not read again by this library), 1 = plain
+// write-back (the fused inverse + select kernel touches the lines again while they are in L2), 2 = plain with an
+// L2 evict_last policy.
 #ifdef MVTB_EMU
-__device__ __forceinline__ void st_stream2(float* p, float a, float b) { p[0] = a; p[1] = b; }
+template <int STORE>
+__device__ __forceinline__ void st_out2(float* p, float a, float b, unsigned long long) { p[0] = a; p[1] = b; }
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() { return 0; }
 #else
-__device__ __forceinline__ void st_stream2(float* p, float a, float b) { __stcs((float2*)p, make_float2(a, b)); }
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+template <int STORE>
+__device__ __forceinline__ void st_out2(float* p, float a, float b, unsigned long long pol) {
+    if (STORE == 0) __stcs((float2*)p, make_float2(a, b));
+    else if (STORE == 1) *(float2*)p = make_float2(a, b);
+    else asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(a), "f"(b), "l"(pol) : "memory");
+}
 #endif
 
-template <int NF>
-__global__ void __launch_bounds__(256, 2)
-k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
-             const BlVol* __restrict__ vols, int vol_base, int shared_desc,
-             float* __restrict__ minmax, int vols_per_sample) {
+__device__ __forceinline__ float min3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// The rows of quads q0 .. q1-1 (and, when `special`, rows 0, H/2, H/4, 3H/4) of this thread's two adjacent columns.
+// sc: (cos, sin) table rows 0 .. H/2; seh: [MVTB_BL_MAX_PW][H/2+1] exp(+2 pi i fh h / H) of this volume's plane waves;
+// yv / ov: this thread's first column in the volume's Y rows / output rows.
+template <int NF, int STORE>
+__device__ __forceinline__ void bl_inv_h4v_cols(const float* __restrict__ sc, const cf* __restrict__ seh, const cf* __restrict__ yv,
+                                                float* __restrict__ ov, const BlGeom& g, const BlVol& bv, int col,
+                                                bool ok, int q0, int q1, bool special, unsigned long long pol,
+                                                float& lo, float& hi) {
     constexpr int NT = BlDims<NF>::NT;
-    MVTB_DYN_SMEM(smem_raw);
     const int H = g.H, H2 = H / 2, H4 = H / 4;
     const int NC = (int)g.NC;
-    float* sc = (float*)smem_raw;
-    cf* seh = (cf*)(sc + (H2 + 1) * NT);
-    const int tid = threadIdx.x;
-    const int vol = blockIdx.x / n_cblocks;
-    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
     const int npw = bv.npw;
-    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
-    for (int e = tid; e < MVTB_BL_MAX_PW * (H2 + 1); e += blockDim.x) {
-        const int s = e / (H2 + 1), h = e - s * (H2 + 1);
-        float c_ = 0.f, s_ = 0.f;
-        if (s < npw) bl_unit32(bv.pw[s].fh, h, H, &c_, &s_);
-        seh[e] = cmk(c_, s_);
-    }
-    __syncthreads();
     bool podd[MVTB_BL_MAX_PW];
     MVTB_UNROLL
     for (int s = 0; s < MVTB_BL_MAX_PW; ++s) podd[s] = s < npw && (bv.pw[s].fh & 1);
-
-    int col = ((blockIdx.x - vol * n_cblocks) * blockDim.x + tid) * 2;
-    const bool ok = col < NC;
-    if (!ok) col = NC - 2;
-    float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
     float2 y2[2][NF];
     float2 E[2][MVTB_BL_MAX_PW];
-    {
-        const cf* yv = Y + (size_t)vol * NF * NC + col;
+    MVTB_UNROLL
+    for (int f = 0; f < NF; ++f) {
+        const float4 y = *reinterpret_cast<const float4*>(yv + (size_t)f * NC);
+        const float cfw = f == 0 ? 1.f : 2.f;
+        y2[0][f] = make_float2(cfw * y.x, cfw * y.y);
+        y2[1][f] = make_float2(cfw * y.z, cfw * y.w);
+    }
+    MVTB_UNROLL
+    for (int k = 0; k < 2; ++k) {
+        const int w = (col + k) / g.D, d = (col + k) - w * g.D;
         MVTB_UNROLL
-        for (int f = 0; f < NF; ++f) {
-            const float4 y = *reinterpret_cast<const float4*>(yv + (size_t)f * NC);
-            const float cfw = f == 0 ? 1.f : 2.f;
-            y2[0][f] = make_float2(cfw * y.x, cfw * y.y);
-            y2[1][f] = make_float2(cfw * y.z, cfw * y.w);
-        }
-        MVTB_UNROLL
-        for (int k = 0; k < 2; ++k) {
-            const int w = (col + k) / g.D, d = (col + k) - w * g.D;
-            MVTB_UNROLL
-            for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
-                E[k][s] = make_float2(0.f, 0.f);
-                if (s < npw) {
-                    float cw, sw, cd, sd;
-                    bl_unit32(bv.pw[s].fw, w, g.W, &cw, &sw);
-                    bl_unit32(bv.pw[s].fd, d, g.D, &cd, &sd);
-                    const float amp = bv.pw[s].amp;
-                    E[k][s] = make_float2(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
-                }
+        for (int s = 0; s < MVTB_BL_MAX_PW; ++s) {
+            E[k][s] = make_float2(0.f, 0.f);
+            if (s < npw) {
+                float cw, sw, cd, sd;
+                bl_unit32(bv.pw[s].fw, w, g.W, &cw, &sw);
+                bl_unit32(bv.pw[s].fd, d, g.D, &cd, &sd);
+                const float amp = bv.pw[s].amp;
+                E[k][s] = make_float2(amp * (cw * cd - sw * sd), amp * (sw * cd + cw * sd));
             }
         }
     }
-    float* ov = out + (size_t)vol * H * NC + col;
-    {
+    if (special) {
         float2 cs[NF];
         bl_row<NF>(sc + H4 * NT, cs);
         float v0[2], vn[2], vq[2], v3q[2];
@@ -397,18 +395,17 @@ k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_
             hi = fmaxf(fmaxf(hi, v0[k]), fmaxf(vn[k], fmaxf(vq[k], v3q[k])));
         }
         if (ok) {
-            st_stream2(ov, v0[0], v0[1]);
-            st_stream2(ov + (size_t)H2 * NC, vn[0], vn[1]);
-            st_stream2(ov + (size_t)H4 * NC, vq[0], vq[1]);
-            st_stream2(ov + (size_t)(H - H4) * NC, v3q[0], v3q[1]);
+            st_out2<STORE>(ov, v0[0], v0[1], pol);
+            st_out2<STORE>(ov + (size_t)H2 * NC, vn[0], vn[1], pol);
+            st_out2<STORE>(ov + (size_t)H4 * NC, vq[0], vq[1], pol);
+            st_out2<STORE>(ov + (size_t)(H - H4) * NC, v3q[0], v3q[1], pol);
         }
     }
-    float* pa = ov + NC;
-    float* pb = ov + (size_t)(H - 1) * NC;
-    float* pc = ov + (size_t)(H2 - 1) * NC;
-    float* pd = ov + (size_t)(H2 + 1) * NC;
-    const int nq = H4 - 1;
-    for (int h = 1; h <= nq; ++h) {
+    float* pa = ov + (size_t)q0 * NC;
+    float* pb = ov + (size_t)(H - q0) * NC;
+    float* pc = ov + (size_t)(H2 - q0) * NC;
+    float* pd = ov + (size_t)(H2 + q0) * NC;
+    for (int h = q0; h < q1; ++h) {
         float2 cs[NF];
         bl_row<NF>(sc + h * NT, cs);
         float2 eh[MVTB_BL_MAX_PW];
@@ -431,43 +428,78 @@ k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_
             const float2 sm = add2(pe, po);
             const float2 df = add2(pe, make_float2(-po.x, -po.y));
             v1[k] = sm.x - sm.y; v2[k] = sm.x + sm.y; v3[k] = df.x + df.y; v4[k] = df.x - df.y;
-            lo = fminf(fminf(lo, fminf(v1[k], v2[k])), fminf(v3[k], v4[k]));
-            hi = fmaxf(fmaxf(hi, fmaxf(v1[k], v2[k])), fmaxf(v3[k], v4[k]));
+            lo = min3(lo, fminf(v1[k], v2[k]), fminf(v3[k], v4[k]));
+            hi = max3(hi, fmaxf(v1[k], v2[k]), fmaxf(v3[k], v4[k]));
         }
         if (ok) {
-            st_stream2(pa, v1[0], v1[1]);
-            st_stream2(pb, v2[0], v2[1]);
-            st_stream2(pc, v3[0], v3[1]);
-            st_stream2(pd, v4[0], v4[1]);
+            st_out2<STORE>(pa, v1[0], v1[1], pol);
+            st_out2<STORE>(pb, v2[0], v2[1], pol);
+            st_out2<STORE>(pc, v3[0], v3[1], pol);
+            st_out2<STORE>(pd, v4[0], v4[1], pol);
         }
         pa += NC; pd += NC;
         pb -= NC; pc -= NC;
     }
-    if (minmax != nullptr) {
-        __shared__ float s_lo[32], s_hi[32];
+}
+
+// CTA-wide (min, max) -> one ordered-int atomic pair on mm[0], mm[1] by thread 0; every thread passes one __syncthreads
+__device__ __forceinline__ void bl_block_minmax(float lo, float hi, float* mm) {
+    __shared__ float s_lo[32], s_hi[32];
+    const int tid = threadIdx.x;
+    MVTB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int lane = tid & 31, wp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) { s_lo[wp] = lo; s_hi[wp] = hi; }
+    __syncthreads();
+    if (wp == 0) {
+        lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
+        hi = lane < nw ? s_hi[lane] : __int_as_float((int)0xff800000u);
         MVTB_UNROLL
         for (int o = 16; o > 0; o >>= 1) {
             lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
             hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
         }
-        const int lane = tid & 31, wp = tid >> 5, nw = (blockDim.x + 31) >> 5;
-        if (lane == 0) { s_lo[wp] = lo; s_hi[wp] = hi; }
-        __syncthreads();
-        if (wp == 0) {
-            lo = lane < nw ? s_lo[lane] : __int_as_float(0x7f800000);
-            hi = lane < nw ? s_hi[lane] : __int_as_float((int)0xff800000u);
-            MVTB_UNROLL
-            for (int o = 16; o > 0; o >>= 1) {
-                lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-                hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-            }
-            if (lane == 0) {
-                float* mm = minmax + 2 * ((vol_base + vol) / vols_per_sample);
-                bl_atomic_min(mm, lo);
-                bl_atomic_max(mm + 1, hi);
-            }
+        if (lane == 0) {
+            bl_atomic_min(mm, lo);
+            bl_atomic_max(mm + 1, hi);
         }
     }
+}
+
+template <int NF>
+__global__ void __launch_bounds__(256, 2)
+k_bl_inv_h4v(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cblocks,
+             const BlVol* __restrict__ vols, int vol_base, int shared_desc,
+             float* __restrict__ minmax, int vols_per_sample) {
+    constexpr int NT = BlDims<NF>::NT;
+    MVTB_DYN_SMEM(smem_raw);
+    const int H = g.H, H2 = H / 2, H4 = H / 4;
+    const int NC = (int)g.NC;
+    float* sc = (float*)smem_raw;
+    cf* seh = (cf*)(sc + (H2 + 1) * NT);
+    const int tid = threadIdx.x;
+    const int vol = blockIdx.x / n_cblocks;
+    const BlVol& bv = vols[shared_desc ? 0 : vol_base + vol];
+    const int npw = bv.npw;
+    bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
+    for (int e = tid; e < MVTB_BL_MAX_PW * (H2 + 1); e += blockDim.x) {
+        const int s = e / (H2 + 1), h = e - s * (H2 + 1);
+        float c_ = 0.f, s_ = 0.f;
+        if (s < npw) bl_unit32(bv.pw[s].fh, h, H, &c_, &s_);
+        seh[e] = cmk(c_, s_);
+    }
+    __syncthreads();
+
+    int col = ((blockIdx.x - vol * n_cblocks) * blockDim.x + tid) * 2;
+    const bool ok = col < NC;
+    if (!ok) col = NC - 2;
+    float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
+    bl_inv_h4v_cols<NF, 0>(sc, seh, Y + (size_t)vol * NF * NC + col, out + (size_t)vol * H * NC + col, g, bv, col, ok,
+                           1, H4, true, 0ull, lo, hi);
+    if (minmax != nullptr) bl_block_minmax(lo, hi, minmax + 2 * ((vol_base + vol) / vols_per_sample));
 }
 
 // ------------------------------------------------------------------ forward, quads, cp.async staging ring

@@ -90,6 +90,15 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // ---------------------------------------------------------------- per-axis FFT description
 struct DescDev;
+// voxel_ops.cu: the geometric-gap sampler on its own (table_dev already holds mvtb_sparse_table(p))
+int sparse_sp_launch(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset, float p,
+                     const float* minmax, const unsigned* table_dev, void* stream);
+// salt-and-pepper to run behind the chain (mvtb_kspace_chain_sp_f32); `done` is set by the path that fused it
+struct SpFuse {
+    float p;
+    unsigned long long seed, offset;
+    bool done;
+};
 #define MVTB_MAX_STAGES 12
 // One pass over the shared-memory tile: a radix stage, or two stages fused in registers.  Everything a thread
 // needs is precomputed on the host: with 128-thread CTAs a thread runs only a couple of butterflies per pass, so
@@ -163,6 +172,14 @@ struct mvtb_plan {
     size_t bl_off[3];
     mvtb::cf* bl_ws;                      // band-limited intermediates (Y, G), grown on demand
     size_t bl_ws_bytes;
+    // fused inverse + salt-and-pepper kernel (bandlimited_sp.cuh); the MVTB_IS_* environment variables are for measurements
+    int opt_fusesp;                       // 1: mvtb_kspace_chain_sp_f32 runs the select pass inside the inverse kernel (MVTB_NO_FUSESP=1: after it)
+    int is_chunk;                         // volumes per launch (0: the band-limited default)
+    int is_hs;                            // parts the H range of a column tile is split into
+    int is_lag;                           // select tiles trail their sample's inverse tiles by this many tiles (-1: one wave of CTAs)
+    int is_spread_pct;                    // ... and are spread over this share of a period
+    int is_store;                         // 0 streaming, 1 write-back, 2 write-back + L2 evict_last
+    unsigned* is_sync;                    // queue head + per-sample completion counters
     // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
     void* stage_h[MVTB_STAGE_SLOTS];
     void* stage_d[MVTB_STAGE_SLOTS];

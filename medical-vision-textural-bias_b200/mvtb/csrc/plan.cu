@@ -135,6 +135,12 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->opt_quad = 1;
     p->opt_async = getenv("MVTB_NO_ASYNC") ? 0 : 1;
     p->opt_fusemid = getenv("MVTB_NO_FUSEMID") ? 0 : 1;
+    p->opt_fusesp = getenv("MVTB_NO_FUSESP") ? 0 : 1;
+    p->is_chunk = getenv("MVTB_IS_CHUNK") ? atoi(getenv("MVTB_IS_CHUNK")) : 0;
+    p->is_hs = getenv("MVTB_IS_HS") ? atoi(getenv("MVTB_IS_HS")) : 4;
+    p->is_lag = getenv("MVTB_IS_LAG") ? atoi(getenv("MVTB_IS_LAG")) : -1;
+    p->is_spread_pct = getenv("MVTB_IS_SPREAD") ? atoi(getenv("MVTB_IS_SPREAD")) : 100;
+    p->is_store = getenv("MVTB_IS_STORE") ? atoi(getenv("MVTB_IS_STORE")) : 1;
     p->chunk = chunk_volumes;
     p->device = device;
     p->num_sms = prop.multiProcessorCount;
@@ -348,6 +354,7 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     if (p->table_mem) cudaFree(p->table_mem);
     if (p->bl_tab) cudaFree(p->bl_tab);
     if (p->bl_ws) cudaFree(p->bl_ws);
+    if (p->is_sync) cudaFree(p->is_sync);
     for (int s = 0; s < MVTB_STAGE_SLOTS; ++s) {
         if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
         if (p->stage_d[s]) cudaFree(p->stage_d[s]);
@@ -363,7 +370,7 @@ extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load()
 
 extern "C" const char* mvtb_kernel_name(int kind) {
     static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
-                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "k_rows_wrap", "", "", ""};
+                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "k_rows_wrap", "k_bl_inv_sp", "", ""};
     return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
 }
 

@@ -6,26 +6,9 @@
 #include <math.h>
 
 #include "mvtb_common.cuh"
+#include "philox.cuh"
 
 namespace mvtb {
-
-// ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11)
-struct Philox {
-    static __device__ __forceinline__ uint4 run(uint4 c, uint2 k) {
-        const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-        MVTB_UNROLL
-        for (int r = 0; r < 10; ++r) {
-            const unsigned hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
-            const unsigned hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
-            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-            k.x += W0;
-            k.y += W1;
-        }
-        return c;
-    }
-    // 24-bit uniform in [0, 1): the grid torch.rand's CPU generator also lands on
-    static __device__ __forceinline__ float to_unit(unsigned r) { return (float)(r >> 8) * 5.9604644775390625e-8f; }
-};
 
 __device__ __forceinline__ void philox_group(uint64_t seed, uint64_t ctr, float* u4) {
     uint4 c = make_uint4((unsigned)ctr, (unsigned)(ctr >> 32), 0u, 0u);
@@ -469,20 +452,12 @@ extern "C" int mvtb_sparse_table(float p, unsigned* table_out) {
     return MVTB_OK;
 }
 
-extern "C" int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset,
-                                           float p, const float* minmax, unsigned* table_dev, void* stream) {
-    if (!x || !minmax || !table_dev) { set_error("salt_pepper_sparse: null argument"); return MVTB_EINVAL; }
-    if (n_samples < 0 || n_samples > 65535) { set_error("salt_pepper_sparse: n_samples=%d", n_samples); return MVTB_EINVAL; }
-    if (!(p >= 0.f && p <= 1.f)) { set_error("salt_pepper_sparse: p=%g outside [0,1]", (double)p); return MVTB_EINVAL; }
-    if (n_samples == 0 || n_per_sample == 0) return MVTB_OK;
+namespace mvtb {
+int sparse_sp_launch(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset, float p,
+                     const float* minmax, const unsigned* table_dev, void* stream) {
+    if (p == 0.f || n_samples == 0 || n_per_sample == 0) return MVTB_OK;   // T = 0 everywhere: no voxel is ever selected
     const size_t bps = (n_per_sample + MVTB_SP_BLOCK - 1) / MVTB_SP_BLOCK;
     if (bps > 0x7fffffffull) { set_error("salt_pepper_sparse: sample too large"); return MVTB_EUNSUPPORTED; }
-    unsigned host_table[MVTB_SP_BLOCK];
-    int rc = mvtb_sparse_table(p, host_table);
-    if (rc != MVTB_OK) return rc;
-    // 1 KB table: a pageable async copy is staged by the runtime before this call returns
-    MVTB_CUDA(cudaMemcpyAsync(table_dev, host_table, sizeof(host_table), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    if (p == 0.f) return MVTB_OK;                      // T = 0 everywhere: no voxel is ever selected
     const unsigned per_cta = (unsigned)(kSpThreadsSparse * kSpNB);
     const unsigned gx = (unsigned)((bps + per_cta - 1) / per_cta);
     const double l2q = log2(1.0 - (double)p);          // -inf for p = 1: the guess is then 0 and the table decides
@@ -491,7 +466,7 @@ extern "C" int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_
     do {                                                                                                          \
         auto kern = k_salt_pepper_sparse<CAP>;                                                                    \
         MVTB_LAUNCH(kern, dim3(gx, (unsigned)n_samples), dim3(kSpThreadsSparse), 0, stream, x, n_per_sample,      \
-                    (unsigned)bps, (const unsigned*)table_dev, inv_log2q, seed, offset, minmax);                  \
+                    (unsigned)bps, table_dev, inv_log2q, seed, offset, minmax);                                   \
     } while (0)
     if (p <= 0.08f) MVTB_SPARSE_LAUNCH(40);
     else if (p <= 0.16f) MVTB_SPARSE_LAUNCH(64);
@@ -499,6 +474,22 @@ extern "C" int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_
 #undef MVTB_SPARSE_LAUNCH
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;
+}
+}  // namespace mvtb
+
+extern "C" int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset,
+                                           float p, const float* minmax, unsigned* table_dev, void* stream) {
+    if (!x || !minmax || !table_dev) { set_error("salt_pepper_sparse: null argument"); return MVTB_EINVAL; }
+    if (n_samples < 0 || n_samples > 65535) { set_error("salt_pepper_sparse: n_samples=%d", n_samples); return MVTB_EINVAL; }
+    if (!(p >= 0.f && p <= 1.f)) { set_error("salt_pepper_sparse: p=%g outside [0,1]", (double)p); return MVTB_EINVAL; }
+    if (n_samples == 0 || n_per_sample == 0) return MVTB_OK;
+    unsigned host_table[MVTB_SP_BLOCK];
+    int rc = mvtb_sparse_table(p, host_table);
+    if (rc != MVTB_OK) return rc;
+    // 1 KB table: a pageable async copy is staged by the runtime before this call returns (mvtb_kspace_chain_sp_f32
+    // sends its table through the plan's pinned staging ring instead)
+    MVTB_CUDA(cudaMemcpyAsync(table_dev, host_table, sizeof(host_table), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return sparse_sp_launch(x, n_per_sample, n_samples, seed, offset, p, minmax, table_dev, stream);
 }
 
 extern "C" int mvtb_wrap_fold_f32(const float* in, float* out, int n_volumes, int H, int W, int D, float alpha, void* stream) {

@@ -116,6 +116,37 @@ def kspace_chain(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc]
     return (y, mm) if want_minmax else y
 
 
+def kspace_chain_sp(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc], p: float, *, seed: int = 0,
+                    offset: int = 0, vols_per_sample: int = 1, out: Optional[torch.Tensor] = None):
+    """kspace_chain followed by the sparse salt-and-pepper sampler, as ONE library call (mvtb_kspace_chain_sp_f32):
+    the same result as kspace_chain(..., want_minmax=True) + salt_pepper(..., sparse=True), bit for bit.  On the
+    band-limited path the select pass runs inside the inverse kernel while the output is still in L2.
+    `offset` counts 256-voxel blocks (advance it by n_samples * ceil(voxels per sample / 256) per call).
+    Returns (y, minmax[n_samples, 2]); minmax is that of the chain's output before the select."""
+    L = _lib.lib()
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("kspace_chain_sp expects a contiguous float32 CUDA tensor (use functional.to_device)")
+    if x.dim() < ndim_fft:
+        raise ValueError(f"input of rank {x.dim()} has fewer than ndim_fft={ndim_fft} axes")
+    fft_shape = tuple(x.shape[-ndim_fft:])
+    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    if len(descs) not in (1, nvol):
+        raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
+    if nvol % vols_per_sample:
+        raise ValueError(f"{nvol} volumes are not a whole number of samples of {vols_per_sample}")
+    y = torch.empty_like(x) if out is None else out
+    mm = torch.empty((nvol // vols_per_sample, 2), dtype=torch.float32, device=x.device)
+    if x.numel() == 0:
+        return y, mm
+    plan = get_plan(fft_shape, nvol, x.device)
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_kspace_chain_sp_f32(plan, _ptr(x), _ptr(y), nvol, host.desc_array(descs), len(descs), _ptr(mm),
+                                        int(vols_per_sample), C.c_float(p), C.c_uint64(seed & (2 ** 64 - 1)),
+                                        C.c_uint64(offset & (2 ** 64 - 1)), _stream(x.device))
+    _lib.check(L, rc)
+    return y, mm
+
+
 def logabs_mean25(x: torch.Tensor, ndim_fft: int) -> torch.Tensor:
     """2.5 * mean(log(|fftn(x)| + 1e-10)) per volume, float32 on x.device (F:932-933, F:1127-1129)."""
     L = _lib.lib()
@@ -227,5 +258,7 @@ def chain127(x: torch.Tensor, *, r: float, spike_idx: Optional[Sequence[Sequence
         descs.extend([d] * C_)
     if p is None:
         return kspace_chain(x, 3, descs)
+    if sparse and u is None:                          # one call: the select pass rides on the inverse kernel
+        return kspace_chain_sp(x, 3, descs, p, seed=seed, offset=offset, vols_per_sample=C_)[0]
     y, mm = kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=C_)
     return salt_pepper(y, p, u=u, seed=seed, offset=offset, n_samples=B_, mm=mm, out=y, sparse=sparse)

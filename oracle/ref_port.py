@@ -240,6 +240,29 @@ def chain_127(x: torch.Tensor, r: float, idx, intensity: float, alpha: float, p:
     return y
 
 
+def chain_127_exact_phase(x: torch.Tensor, r: float, idx, intensity: float, alpha: float) -> torch.Tensor:
+    """disk -> plane-wave spike -> wrap (F:244-251, F:381-392, F:503-515) in float64 with the ONE place where the
+    reference's result is rounding noise made exact.
+
+    In the 125/126/127 chains the spike lands on a bin the disk stage set to zero.  The reference then reads
+    `angle(k)` of the round-trip residue at that bin (F:385): its own fp32 and fp64 runs differ by rel-L2 ~ 1
+    (SURVEY section 0).  In exact arithmetic the bin is 0 and `angle(0) = 0`, which is what the CUDA kernels compute.
+    This restatement runs the three stages in float64 and, when the spike's bin is outside the disk, sets that bin
+    of the disk stage's spectrum to exactly 0 before the spike stage -- nothing else differs from `chain_127`.
+    tests/test_oracle_golden.py ties it to the unmodified reference: equal modulo the +-f_s plane wave, with the
+    injected amplitude equal."""
+    xd = x.to(torch.float64)
+    k = kspace(xd, 3)
+    k = k * disk_binary_mask(k.shape, r, 3, False).to(torch.float64)
+    # the reference goes back to the image and forward again between stages; in exact arithmetic that is the identity
+    la = k.abs().log()
+    ph = k.angle()                                       # angle(0) = 0 for the exactly-zero masked bins
+    la[:, idx[0], idx[1], idx[2]] = intensity
+    k2 = la.exp() * torch.exp(1j * ph)
+    y = image_real(k2, 3)
+    return wrap_artifact(y, alpha)
+
+
 # --------------------------------------------------------------------------- synthetic data
 
 

@@ -73,6 +73,8 @@ void* warp_slot();   // 32 x 16-byte exchange slots of the calling thread's warp
 #define gridDim (cuemu::g_gridDim)
 static const int warpSize = 32;
 
+static inline void __threadfence() {}
+static inline void __nanosleep(unsigned) {}
 static inline void __syncthreads() { cuemu::block_barrier(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { cuemu::warp_barrier(); }
 

@@ -1,0 +1,172 @@
+"""mvtb_kspace_chain_sp_f32 on the GPU: the 127 chain with the select pass inside the persistent inverse kernel.
+
+  * bit-identical to mvtb_kspace_chain_f32 + mvtb_salt_pepper_sparse_f32 (small, ragged and BASELINE sizes);
+  * at BASELINE size the voxels it changed are fed back to the ORACLE's SaltAndPepper as its uniform field
+    (north_star: "bit-exact given the same sampled coordinates"): torch.equal, values = min/2, max/2 of the whole
+    sample, everything else untouched, hit rate Bernoulli(p);
+  * the k-space part of the benchmarked configuration (spike on a bin the disk zeroed) against the float64
+    exact-phase oracle at 1e-5.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def _descs(shape3, n, r=12.5, intensity=15.0, alpha=0.5, seed0=0):
+    from mvtb import _lib, host
+    thr = host.disk_threshold(r, shape3)
+    shell = host.ellipsoid_shell(tuple(shape3), 55., 55., 30.)
+    idxs, out = [], []
+    for i in range(n):
+        idx = tuple(int(v) for v in shell[np.random.RandomState(seed0 + i).randint(0, len(shell))])
+        idxs.append(idx)
+        out.append(host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr,
+                                  spikes=[(idx, host.exp_f32(intensity))], wrap_alpha=alpha))
+    return out, idxs
+
+
+def _kinds(plan):
+    from mvtb import _lib
+    L = _lib.lib()
+    ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+    _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+    _lib.check(L, L.mvtb_plan_profile(plan, 0))
+    return {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
+
+
+@pytest.mark.parametrize("shape,vps,p", [((6, 1, 64, 48, 40), 1, 0.05), ((3, 2, 128, 128, 64), 2, 0.15),
+                                         ((5, 1, 32, 36, 31), 1, 0.35), ((2, 4, 64, 64, 30), 4, 0.08)])
+def test_fused_equals_two_calls(cuda_device, shape, vps, p):
+    from mvtb import _lib, functional as Fn, host
+    from oracle import ref_port as P
+    x = torch.stack([P.synthetic_volume(i, shape[1:]) for i in range(shape[0])]).to(cuda_device)
+    thr = host.disk_threshold(6.5, shape[-3:])
+    descs = []
+    for b in range(shape[0]):
+        idx = (shape[2] // 2 + 9 + b % 3, shape[3] // 2 - 11, shape[4] // 2 + 8)       # outside the ball: plane waves
+        d = host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=[(idx, host.exp_f32(9.0))], wrap_alpha=0.25)
+        descs.extend([d] * vps)
+    y3, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=vps)
+    want = Fn.salt_pepper(y3, p, seed=31, offset=12345, n_samples=shape[0], mm=mm, sparse=True)
+    plan = Fn.get_plan(shape[-3:], shape[0] * vps, cuda_device)
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_profile(plan, 1))
+    got, mm2 = Fn.kspace_chain_sp(x, 3, descs, p, seed=31, offset=12345, vols_per_sample=vps)
+    torch.cuda.synchronize()
+    kinds = _kinds(plan)
+    assert "k_bl_inv_sp" in kinds and "k_bl_inv_h" not in kinds
+    assert torch.equal(mm, mm2)
+    assert torch.equal(got, want)
+    assert not torch.equal(got, y3)
+    # in place
+    z = x.clone()
+    got2, _ = Fn.kspace_chain_sp(z, 3, descs, p, seed=31, offset=12345, vols_per_sample=vps, out=z)
+    assert got2.data_ptr() == z.data_ptr() and torch.equal(z, want)
+
+
+@pytest.mark.parametrize("hs,lag,store", [(1, 0, 0), (2, 37, 2), (4, 2000, 1), (8, 300, 1)])
+def test_queue_shapes_do_not_change_the_result(cuda_device, monkeypatch, hs, lag, store):
+    """Tile split, lag of the select tiles and store policy are scheduling choices: same bits."""
+    from mvtb import functional as Fn
+    from oracle import ref_port as P
+    shape3 = (128, 128, 64)
+    x = torch.stack([P.synthetic_volume(40 + i, (1,) + shape3) for i in range(7)]).to(cuda_device)
+    descs, _ = _descs(shape3, 7)
+    want, _ = Fn.kspace_chain_sp(x, 3, descs, 0.05, seed=5, offset=0)
+    monkeypatch.setenv("MVTB_IS_HS", str(hs))
+    monkeypatch.setenv("MVTB_IS_LAG", str(lag))
+    monkeypatch.setenv("MVTB_IS_STORE", str(store))
+    monkeypatch.setenv("MVTB_IS_CHUNK", "3")
+    Fn._destroy_plans()                                     # the options are read when a plan is created
+    got, _ = Fn.kspace_chain_sp(x, 3, descs, 0.05, seed=5, offset=0)
+    torch.cuda.synchronize()
+    Fn._destroy_plans()
+    assert torch.equal(got, want)
+
+
+def test_baseline_size_select_against_the_oracle(cuda_device):
+    """BASELINE cfg2 at full size, 64 x (1 x 240 x 240 x 155), as benchmarked (fused call, sparse sampler, p = 0.05):
+    rebuild a uniform field from the coordinates the kernel hit and hand it, with the chain's own stage-3 output,
+    to oracle.ref_port.salt_and_pepper (F:465-482): the 64 volumes must be equal bit for bit."""
+    from mvtb import functional as Fn
+    from oracle import ref_port as P
+    shape3 = (240, 240, 155)
+    B_, p = 64, 0.05
+    n = shape3[0] * shape3[1] * shape3[2]
+    x = torch.empty((B_, 1) + shape3, dtype=torch.float32, device=cuda_device)
+    for b in range(B_):
+        x[b] = P.synthetic_volume(b, (1,) + shape3).to(cuda_device)
+    descs, _ = _descs(shape3, B_)
+    y3 = Fn.kspace_chain(x, 3, descs)
+    y4, mm = Fn.kspace_chain_sp(x, 3, descs, p, seed=2024, offset=0)
+    torch.cuda.synchronize()
+    total_hits = 0
+    for b in range(B_):
+        a3, a4 = y3[b].cpu(), y4[b].cpu()
+        lo, hi = a3.min() / 2, a3.max() / 2
+        assert float(mm[b, 0]) == float(a3.min()) and float(mm[b, 1]) == float(a3.max())
+        hit = a4 != a3
+        vals = a4[hit]
+        is_lo = vals == lo
+        assert bool((is_lo | (vals == hi)).all())
+        u = torch.ones_like(a3)
+        uh = torch.where(is_lo, torch.tensor(p / 4), torch.tensor(3 * p / 4))
+        u[hit] = uh
+        assert torch.equal(P.salt_and_pepper(a3, p, u), a4)
+        total_hits += int(hit.sum())
+        frac = float(hit.float().mean())
+        assert abs(frac - p) < 5 * np.sqrt(p * (1 - p) / n)
+    assert abs(total_hits / (B_ * n) - p) < 5 * np.sqrt(p * (1 - p) / (B_ * n))
+
+
+def test_baseline_size_fused_equals_two_calls(cuda_device):
+    from mvtb import functional as Fn
+    from oracle import ref_port as P
+    shape3 = (240, 240, 155)
+    B_ = 12
+    x = torch.stack([P.synthetic_volume(100 + b, (1,) + shape3) for b in range(B_)]).to(cuda_device)
+    descs, _ = _descs(shape3, B_, seed0=100)
+    y3, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True)
+    want = Fn.salt_pepper(y3, 0.05, seed=9, offset=77, n_samples=B_, mm=mm, sparse=True)
+    got, mm2 = Fn.kspace_chain_sp(x, 3, descs, 0.05, seed=9, offset=77)
+    assert torch.equal(mm, mm2) and torch.equal(got, want)
+    # 4-channel samples (BASELINE cfg3's shape): one select field and one (min, max) per 4 volumes
+    x4 = x.reshape(3, 4, *shape3)
+    d4 = [descs[4 * (i // 4)] for i in range(B_)]
+    y3, mm = Fn.kspace_chain(x4, 3, d4, want_minmax=True, vols_per_sample=4)
+    want = Fn.salt_pepper(y3, 0.15, seed=9, offset=0, n_samples=3, mm=mm, sparse=True)
+    got, mm2 = Fn.kspace_chain_sp(x4, 3, d4, 0.15, seed=9, offset=0, vols_per_sample=4)
+    assert torch.equal(mm, mm2) and torch.equal(got, want)
+
+
+@pytest.mark.parametrize("sample", [0, 1, 2])
+def test_cfg2_kspace_part_against_exact_phase_oracle(cuda_device, sample):
+    """The benchmarked configuration puts the spike on a bin the disk zeroed.  Against the float64 oracle that
+    takes angle(0) = 0 there (oracle.ref_port.chain_127_exact_phase; tied to the unmodified reference in
+    tests/test_oracle_golden.py) both paths hold the 1e-5 bar, no projection needed."""
+    from mvtb import functional as Fn, host
+    from oracle import ref_port as P
+    shape = (1, 240, 240, 155)
+    x = P.synthetic_volume(sample, shape)
+    descs, idxs = _descs(shape[1:], 1, seed0=sample)
+    assert sum((i - n // 2) ** 2 for i, n in zip(idxs[0], shape[1:])) > host.disk_threshold(12.5, shape[1:])
+    ref = P.chain_127_exact_phase(x, 12.5, idxs[0], 15.0, 0.5).numpy()
+    y = Fn.kspace_chain(x.to(cuda_device), 3, descs)
+    assert rel_l2(y.cpu().numpy(), ref) <= TOL
+    plan = Fn.get_plan(shape[1:], 1, cuda_device)
+    from mvtb import _lib
+    L = _lib.lib()
+    _lib.check(L, L.mvtb_plan_set_path(plan, 1))
+    try:
+        yg = Fn.kspace_chain(x.to(cuda_device), 3, descs)
+    finally:
+        _lib.check(L, L.mvtb_plan_set_path(plan, 0))
+    assert rel_l2(yg.cpu().numpy(), ref) <= TOL

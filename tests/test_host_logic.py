@@ -124,7 +124,7 @@ def test_cabi_exports_every_declared_symbol():
         from mvtb import build
         build.build_library()
     lib = B.bind(C.CDLL(B.LIB_PATH))          # raises AttributeError on a missing export
-    assert lib.mvtb_version() == 100
+    assert lib.mvtb_version() == 200
     assert C.sizeof(B.ChainDesc) == 32 + 8 * 24 and C.sizeof(B.Spike) == 24
 
 

@@ -108,3 +108,21 @@ def test_reference_notebook_fft_kats():
     tile = torch.tensor([1., 1, 0, 0, 1, 1, 0, 0]).repeat(8, 1)
     k = torch.fft.fftn(tile)
     assert abs(k[0, 0] - 32) < 1e-4 and abs(k[0, 2] - (16 - 16j)) < 1e-4 and abs(k[0, 6] - (16 + 16j)) < 1e-4
+
+
+@pytest.mark.parametrize("name", golden_names("chain127_"))
+def test_exact_phase_oracle_is_the_reference_modulo_the_ill_conditioned_plane_wave(name):
+    """oracle.ref_port.chain_127_exact_phase (float64, angle(0) = 0 where the disk zeroed the spike's bin) against
+    the UNMODIFIED reference's stage-3 output: equal to fp32 rounding when the spike is inside the disk; otherwise
+    equal after removing the +-f_s plane wave from both (the reference's phase there is rounding noise, SURVEY
+    section 0), with the same injected amplitude."""
+    from test_gpu_parity import _remove_plane_wave
+    m, z = load_golden(name)
+    y = P.chain_127_exact_phase(torch.from_numpy(z["x"]), m["r"], m["idx"], m["intensity"], m["alpha"]).numpy()
+    if m["spike_in_ball"]:
+        assert rel_l2(y, z["y3"]) <= 1e-6
+    else:
+        ra, aa = _remove_plane_wave(y, m["idx"])
+        rb, ab = _remove_plane_wave(z["y3"], m["idx"])
+        assert rel_l2(ra, rb) <= 1e-6
+        assert np.allclose(aa, ab, rtol=1e-5)
