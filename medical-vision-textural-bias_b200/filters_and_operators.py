@@ -501,7 +501,7 @@ class KSpaceSpikeNoise(Transform, Fourier):
         else:
             pairs = [(self.loc, default if intensity is None else intensity)]
 
-        pairs = [(tuple(int(i) for i in idx), val) for idx, val in pairs]
+        pairs = [(self._wrap_negative(tuple(int(i) for i in idx), x.shape), val) for idx, val in pairs]
         if all(len(idx) == rank - 1 for idx, _ in pairs) and rank in (3, 4):
             # every spike hits all channels (F:980-983): one descriptor for the whole stack, however many channels
             shared = []
@@ -530,6 +530,19 @@ class KSpaceSpikeNoise(Transform, Fourier):
                 descs.append(made[key])
         out = Fn.back(Fn.kspace_chain(x, n_dims, descs), src)
         return out if self.as_tensor_output else out.cpu().detach().numpy()
+
+
+    @staticmethod
+    def _wrap_negative(idx: Tuple[int, ...], shape) -> Tuple[int, ...]:
+        """Negative indices count from the end, as in the reference's `k[idx] = val` (F:975-983; its bounds check
+        F:958-962 only looks at the largest index); beyond -N torch raises IndexError, and so does this."""
+        dims = tuple(shape)[len(shape) - len(idx):]
+        out = []
+        for d, (i, n) in enumerate(zip(idx, dims)):
+            if i < -int(n):
+                raise IndexError(f"index {i} is out of bounds for dimension {d + len(shape) - len(idx)} with size {int(n)}")
+            out.append(i + int(n) if i < 0 else i)
+        return tuple(out)
 
 
 class RandKSpaceSpikeNoise(RandomizableTransform, Fourier):

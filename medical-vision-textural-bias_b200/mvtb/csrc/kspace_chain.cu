@@ -484,7 +484,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
                         const bool isp = ((mpos >> sI) & 1u) && im == d.sp[sI].idx[axis];
                         const bool isn = ((mneg >> sI) & 1u) && imn == d.sp[sI].idx[axis];
                         if (!isp && !isn) continue;
-                        const float ms = (float)d.sp[sI].mask_at_spike;
+                        const float ms = d.sp[sI].meff_at_spike;
                         if (isp && isn) {                 // self-conjugate bin: Re(new)
                             const cf ko = cscale(K, ms);
                             const cf nw = spike_value(ko, d.sp[sI].amp);
@@ -631,19 +631,25 @@ int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
     d->wrap_alpha = u->wrap_alpha;
     d->wrap_naxes = u->wrap_naxes;
     for (int s = 0; s < u->n_spikes; ++s) {
-        long long q = 0;
+        long long q = 0, qneg = 0;                                 // mask distance of the bin and of its mirror -f_s
         for (int a = 0; a < p->ndim; ++a) {
             const int idx = u->spikes[s].idx[p->ndim - 1 - a];     // user order: outermost first
             const int n = p->shape[a];
             if (idx < 0 || idx >= n) { set_error("chain: spike %d index %d out of bounds for axis of length %d", s, idx, n); return MVTB_EINVAL; }
             d->sp[s].idx[a] = idx;
             if (a < d->mask_ndim) {
+                const int ineg = (2 * (n / 2) - idx + n) % n;
                 const long long dd = d->mask_kind == MVTB_MASK_DISK ? (long long)(idx - n / 2) : (long long)(2 * idx - (n - 1));
+                const long long dn = d->mask_kind == MVTB_MASK_DISK ? (long long)(ineg - n / 2) : (long long)(2 * ineg - (n - 1));
                 q += dd * dd;
+                qneg += dn * dn;
             }
         }
         d->sp[s].amp = u->spikes[s].amplitude;
-        d->sp[s].mask_at_spike = d->mask_kind == MVTB_MASK_NONE ? 1 : (((q <= d->thr) ? 1 : 0) ^ d->inside_off);
+        // The mask stage returns a REAL image, whose spectrum at f_s is M_eff(f_s) K; that is the bin the
+        // spike stage reads.  A centred mask on an even axis has M(f) != M(-f) on its boundary shell.
+        if (d->mask_kind == MVTB_MASK_NONE) d->sp[s].meff_at_spike = 1.f;
+        else d->sp[s].meff_at_spike = 0.5f * (float)((((q <= d->thr) ? 1 : 0) ^ d->inside_off) + (((qneg <= d->thr) ? 1 : 0) ^ d->inside_off));
         for (int s2 = 0; s2 < s; ++s2) {
             bool same = true;
             for (int a = 0; a < p->ndim; ++a) same = same && d->sp[s2].idx[a] == d->sp[s].idx[a];

@@ -128,7 +128,7 @@ struct AxisDev {
 struct SpikeDev {
     int idx[MVTB_MAX_FFT_DIMS];  // shifted index per FFT axis, axis 0 = LAST (contiguous) axis
     float amp;
-    int mask_at_spike;           // M(f_s) in {0,1}
+    float meff_at_spike;         // (M(f_s) + M(-f_s)) / 2 in {0, 1/2, 1}: the weight of that bin after the mask stage
 };
 struct DescDev {
     int mask_kind, mask_ndim;

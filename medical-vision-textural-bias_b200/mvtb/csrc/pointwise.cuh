@@ -3,8 +3,9 @@
 //
 // With fftshift-ed index i_d per axis and its negation i'_d = (2 floor(N/2) - i_d) mod N:
 //   M_eff = (M(i) + M(i')) / 2              real part after an asymmetric mask
-//   spike at this bin      : + (new - k_old) / 2,      k_old = M(f_s) K
-//   spike at the conjugate : + conj(new - k_old) / 2,  k_old = M(f_s) conj K   (K(f_s) = conj K(-f_s))
+//   spike at this bin      : + (new - k_old) / 2,      k_old = M_eff(f_s) K  (what the previous stage's REAL output
+//                                                       holds at that bin: GibbsNoise -> KSpaceSpikeNoise in sequence)
+//   spike at the conjugate : + conj(new - k_old) / 2,  k_old = M_eff(f_s) conj K   (K(f_s) = conj K(-f_s))
 //   self-conjugate spike   : bin becomes Re(new)
 //   new = amp * k_old / |k_old|  (amp if k_old == 0: angle(0) = 0, F:384/F:928)
 //   wrap: x alpha for every odd i_d among the trailing wrap_naxes axes (F:509-511)
@@ -54,7 +55,7 @@ __device__ __forceinline__ cf pointwise_bin(const DescDev& d, int ndim, const in
             isn = isn && ineg[a] == d.sp[s].idx[a];
         }
         if (!isp && !isn) continue;
-        const float ms = (float)d.sp[s].mask_at_spike;
+        const float ms = d.sp[s].meff_at_spike;
         if (isp && isn) {
             const cf ko = cscale(K, ms);
             const cf nw = pw_spike_value(ko, d.sp[s].amp);

@@ -7,7 +7,9 @@ every leading axis is a batch of independent volumes.
 """
 import atexit
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+import threading
+from collections import OrderedDict
+from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import numpy as np
 import torch
@@ -19,7 +21,24 @@ import os
 # plan workspace: ~2 half-spectra of 240x240x155 for the general path (L2-resident between its kernels);
 # the band-limited path fits ~16 volumes of intermediates in the same bytes.  MVTB_WS_MB overrides.
 _WS_TARGET_BYTES = int(os.environ.get("MVTB_WS_MB", "80")) << 20
-_plans = {}
+# A plan owns one workspace and one ring of staging slots, so it serves one stream at a time (include/mvtb.h).
+# Plans are therefore cached per (thread, device, stream, shape, chunk): two streams, or two Python threads (ctypes
+# releases the GIL during a call), never share one.  Each thread keeps at most _MAX_PLANS of them, least recently
+# used first out (a pipeline fed with random crop sizes would otherwise grow device memory without bound);
+# MVTB_MAX_PLANS overrides.
+_MAX_PLANS = max(1, int(os.environ.get("MVTB_MAX_PLANS", "12")))
+_tls = threading.local()
+_registry_lock = threading.Lock()
+_registry = []                      # every thread's cache, for the exit hook
+
+
+def _cache() -> "OrderedDict":
+    c = getattr(_tls, "plans", None)
+    if c is None:
+        c = _tls.plans = OrderedDict()
+        with _registry_lock:
+            _registry.append(c)
+    return c
 
 
 def require_cuda() -> None:
@@ -36,55 +55,86 @@ def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
-def to_device(x, device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.device]:
-    """float32 contiguous CUDA view/copy of x, plus the device x came from (results go back there)."""
+class Origin(NamedTuple):
+    """Where a transform's input came from: results go back to that device, in that precision."""
+    device: torch.device
+    dtype: torch.dtype
+
+
+def to_device(x, device: Optional[torch.device] = None) -> Tuple[torch.Tensor, Origin]:
+    """float32 contiguous CUDA view/copy of x, plus its origin for `back()`.
+
+    The kernels compute in float32, the precision of every reference pipeline.  A float64 input (a tensor made from
+    a default numpy array, say), for which the reference would run a complex128 FFT and return float64, is computed
+    in float32 here and handed back as float64; integer inputs come back as float32, as from the reference's FFT."""
     require_cuda()
     if isinstance(x, np.ndarray):
         x = torch.as_tensor(x)
     if not isinstance(x, torch.Tensor):
         raise TypeError(f"expected a torch.Tensor or numpy array, got {type(x).__name__}")
+    if x.is_complex():
+        raise TypeError(f"mvtb transforms take real images (got {x.dtype})")
+    org = Origin(x.device, x.dtype if x.dtype == torch.float64 else torch.float32)
     if x.dtype != torch.float32:
-        raise TypeError(f"mvtb kernels are float32-only (got {x.dtype}); the reference pipelines are float32 as well")
-    src = x.device
+        x = x.to(torch.float32)
     if x.is_cuda:
-        return x.contiguous(), src
+        return x.contiguous(), org
     dev = device or torch.device("cuda", torch.cuda.current_device())
-    return x.contiguous().to(dev, non_blocking=False), src
+    return x.contiguous().to(dev, non_blocking=False), org
 
 
-def back(y: torch.Tensor, src: torch.device) -> torch.Tensor:
-    return y if src == y.device else y.to(src)
+def back(y: torch.Tensor, org) -> torch.Tensor:
+    if isinstance(org, Origin):
+        y = y if org.device == y.device else y.to(org.device)
+        return y if org.dtype == y.dtype else y.to(org.dtype)
+    return y if org == y.device else y.to(org)
 
 
 def get_plan(fft_shape: Sequence[int], n_volumes: int, dev: torch.device):
+    """The calling thread's plan for this shape on the current stream of `dev` (created on first use)."""
     fft_shape = tuple(int(s) for s in fft_shape)
     nh = fft_shape[-1] // 2 + 1
     half_bytes = 8 * nh * int(np.prod(fft_shape[:-1]))
     chunk = int(max(1, min(n_volumes, _WS_TARGET_BYTES // max(half_bytes, 1))))
     if chunk > 8:
         chunk = 1 << (chunk.bit_length() - 1)        # few distinct plans per shape
-    key = (dev.index, fft_shape, chunk)
-    h = _plans.get(key)
-    if h is None:
-        L = _lib.lib()
-        h = C.c_void_p()
-        shp = (C.c_int * len(fft_shape))(*fft_shape)
-        _lib.check(L, L.mvtb_plan_create(C.byref(h), len(fft_shape), shp, chunk, dev.index))
-        if os.environ.get("MVTB_PATH"):              # measurements: 1 = general FFT path only, 2 = pair kernels
-            _lib.check(L, L.mvtb_plan_set_path(h, int(os.environ["MVTB_PATH"])))
-        _plans[key] = h
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, fft_shape, chunk)
+    cache = _cache()
+    h = cache.get(key)
+    if h is not None:
+        cache.move_to_end(key)
+        return h
+    L = _lib.lib()
+    while len(cache) >= _MAX_PLANS:                   # evict this thread's least recently used plan
+        _, old = cache.popitem(last=False)
+        L.mvtb_plan_destroy(old)                      # waits for the device, then frees tables and workspace
+    h = C.c_void_p()
+    shp = (C.c_int * len(fft_shape))(*fft_shape)
+    _lib.check(L, L.mvtb_plan_create(C.byref(h), len(fft_shape), shp, chunk, dev.index))
+    if os.environ.get("MVTB_PATH"):                  # measurements: 1 = general FFT path only, 2 = pair kernels
+        _lib.check(L, L.mvtb_plan_set_path(h, int(os.environ["MVTB_PATH"])))
+    cache[key] = h
     return h
+
+
+def plan_cache_size() -> int:
+    """Plans currently held for the calling thread."""
+    return len(_cache())
 
 
 @atexit.register
 def _destroy_plans():
-    if _plans and _lib._lib is not None:
-        for h in _plans.values():
+    if _lib._lib is None:
+        return
+    with _registry_lock:
+        caches = list(_registry)
+    for c in caches:
+        for h in list(c.values()):
             try:
                 _lib._lib.mvtb_plan_destroy(h)
             except Exception:  # noqa: BLE001
                 pass
-        _plans.clear()
+        c.clear()
 
 
 def kspace_chain(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc], *, want_minmax: bool = False,

@@ -12,10 +12,9 @@ import torch.nn as nn
 from filters_and_operators import RandKSpaceSpikeNoise
 from mvtb import _lib, functional as Fn, host
 
-try:  # pragma: no cover - MONAI is optional; only the *_UNet compositions need it
-    from monai.networks.nets import UNet
-except Exception:  # noqa: BLE001
-    UNet = None
+# monai.networks.nets.UNet when MONAI is installed, else a plain-torch residual U-Net with the same constructor
+# (mvtb/_monai_compat.py): the network consumes the layers' output and is not part of the hot path
+from mvtb._monai_compat import UNet
 
 
 class Fourier:
@@ -78,12 +77,10 @@ class GibbsNoiseLayer(nn.Module, Fourier):
 
 
 class Gibbs_UNet(nn.Module):
-    """GibbsNoiseLayer(0.5) in front of MONAI's 3-D ResUNet (S:119-139); the argument is ignored, as in the reference."""
+    """GibbsNoiseLayer(0.5) in front of the 3-D ResUNet (S:119-139); the argument is ignored, as in the reference."""
 
     def __init__(self, alpha=None):
         super().__init__()
-        if UNet is None:
-            raise ImportError("Gibbs_UNet needs monai.networks.nets.UNet (MONAI is not installed)")
         self.gibbs = GibbsNoiseLayer(.5)
         self.ResUnet = UNet(dimensions=3, in_channels=1, out_channels=1, channels=(16, 32, 64, 128, 256),
                             strides=(2, 2, 2, 2), num_res_units=2)
@@ -110,8 +107,6 @@ class Spikes_UNet(nn.Module):
 
     def __init__(self, intensity=15):
         super().__init__()
-        if UNet is None:
-            raise ImportError("Spikes_UNet needs monai.networks.nets.UNet (MONAI is not installed)")
         self.spike = spike_layer(intensity)
         self.ResUnet = UNet(dimensions=3, in_channels=1, out_channels=1, channels=(16, 32, 64, 128, 256),
                             strides=(2, 2, 2, 2), num_res_units=2)

@@ -138,3 +138,31 @@ def test_argument_errors():
     assert L.mvtb_kspace_chain_sp_f32(plan.h, emu.ptr(x), emu.ptr(y), 3, arr, 1, None, 1, C.c_float(0.1), 1, 0, None) == B.MVTB_EINVAL
     assert L.mvtb_kspace_chain_sp_f32(plan.h, emu.ptr(x), emu.ptr(y), 3, arr, 1, emu.ptr(mm), 2, C.c_float(0.1), 1, 0, None) == B.MVTB_EINVAL
     assert L.mvtb_kspace_chain_sp_f32(plan.h, emu.ptr(x), emu.ptr(y), 3, arr, 1, emu.ptr(mm), 1, C.c_float(1.5), 1, 0, None) == B.MVTB_EINVAL
+
+
+def test_spike_on_the_boundary_shell_of_a_centred_mask():
+    """GibbsNoise then KSpaceSpikeNoise as ONE descriptor, with the spike on a bin where the centred mask keeps f_s
+    but not -f_s (even axes): the spike stage must read M_eff(f_s) K = K / 2, what the mask stage's real output
+    holds there.  Both chain paths against the oracle's two sequential calls."""
+    import torch
+    from conftest import rel_l2
+    shape = (1, 8, 8, 6)
+    x = P.synthetic_volume(2, shape)
+    x = x + 0.3 * torch.randn(shape, generator=torch.Generator().manual_seed(1))   # energy in every bin
+    alpha = 0.45
+    thr = host.gibbs_threshold(alpha, shape[1:])
+    mask = P.gibbs_mask(shape[1:], alpha)
+    cand = [(i, j, k) for i in range(8) for j in range(8) for k in range(6)
+            if mask[i, j, k] and not mask[(8 - i) % 8, (8 - j) % 8, (6 - k) % 6]]
+    assert cand, "no asymmetric shell bin for this alpha"
+    idx = cand[len(cand) // 2]
+    ref = P.kspace_spike(P.gibbs_noise(x, alpha), idx, 6.0).numpy()
+    d = host.make_desc(mask_kind=B.MASK_CENTRED, mask_ndim=3, mask_thresh=thr, spikes=[(idx, host.exp_f32(6.0))])
+    for general in (True, False):
+        L = emu.lib()
+        plan = emu.Plan(shape[1:], 2)
+        B.check(L, L.mvtb_plan_set_path(plan.h, 1 if general else 0))
+        xn = x.numpy()
+        y = np.empty_like(xn)
+        B.check(L, L.mvtb_kspace_chain_f32(plan.h, emu.ptr(xn), emu.ptr(y), 1, host.desc_array([d]), 1, None, 1, None))
+        assert rel_l2(y, ref) <= 1e-5, (general, rel_l2(y, ref))
