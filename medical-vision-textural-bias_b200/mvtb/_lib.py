@@ -63,6 +63,7 @@ _SYMBOLS = {
     "mvtb_kernel_name": (C.c_char_p, [C.c_int]),
     "mvtb_launch_count": (C.c_ulonglong, []),
     "mvtb_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
+    "mvtb_plan_tc_status": (C.c_int, [C.c_void_p]),
 }
 K_KINDS = 16
 SP_BLOCK = 256

@@ -22,6 +22,7 @@
 // memory as 128-bit broadcasts.  Results are the same numbers the general path produces (same
 // pointwise stage, pointwise.cuh), to fp32 rounding.
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -30,6 +31,7 @@
 
 #include "philox.cuh"
 #include "pointwise.cuh"
+#include "tc_common.cuh"
 
 namespace mvtb {
 
@@ -559,6 +561,7 @@ k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cb
 
 #include "bandlimited_quad.cuh"
 #include "bandlimited_sp.cuh"
+#include "bandlimited_tc.cuh"
 
 // ------------------------------------------------------------------ host side
 size_t bl_workspace_per_volume(const mvtb_plan* p, int F);
@@ -647,6 +650,77 @@ static int bl_make_vol(const mvtb_plan* p, const BlGeom& g, const mvtb_chain_des
     }
     return convert_desc(p, &inbox, &out->d);
 }
+
+#ifndef MVTB_EMU
+// ---- tensor-core H-axis kernels: tensor map of the volume rows, operand tables
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// x viewed as a 2-D fp32 tensor [rows][cols]; box = box_rows x box_cols; no swizzle; out-of-bounds reads give zeros
+static int tc_make_tmap(CUtensorMap* out, const float* base, unsigned long long rows, unsigned long long cols, unsigned box_cols,
+                        unsigned box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        MVTB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr));
+        if (!f || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available in this driver"); return MVTB_EUNSUPPORTED; }
+        fn = (EncodeTiledFn)f;
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {cols * sizeof(float)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return MVTB_EUNSUPPORTED; }
+    return MVTB_OK;
+}
+// ---- operand tables
+static int nf_slot(int nf) {
+    static const int avail[] = {4, 8, 13, 16, 20, 26, 32};
+    for (int i = 0; i < 7; ++i)
+        if (avail[i] == nf) return i;
+    return -1;
+}
+static float tf32_round(float x) {                        // cvt.rna.tf32.f32 on the host: nearest, ties away, 10 mantissa bits
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0x1000u;
+    u &= 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+// B operand of the forward pass, [2][H * N] (hi, lo) in tc::op_offset layout: row 2f = cos(2 pi f h / H), row 2f+1 =
+// -sin(2 pi f h / H) (Y = sum_h x e^{-2 pi i f h / H}), rows >= 2 NF zero; computed in double, split for 3xTF32
+static int tc_fwd_table(mvtb_plan* p, int NF, int N, const float** out) {
+    const int slot = nf_slot(NF);
+    if (slot < 0) return MVTB_EUNSUPPORTED;
+    if (!p->tc_tab_fwd[slot]) {
+        const int H = p->shape[2];
+        std::vector<float> t((size_t)2 * H * N, 0.f);
+        for (int n = 0; n < 2 * NF; ++n)
+            for (int h = 0; h < H; ++h) {
+                const long long m = ((long long)(n / 2) * h) % H;
+                const double ang = 2.0 * M_PI * (double)m / (double)H;
+                const double v = (n & 1) ? -sin(ang) : cos(ang);
+                const float hi = tf32_round((float)v), lo = tf32_round((float)(v - (double)hi));
+                const size_t o = tc::op_offset(n, h, N) / 4;
+                t[o] = hi;
+                t[(size_t)H * N + o] = lo;
+            }
+        MVTB_CUDA(cudaMalloc((void**)&p->tc_tab_fwd[slot], t.size() * sizeof(float)));
+        MVTB_CUDA(cudaMemcpy(p->tc_tab_fwd[slot], t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (!p->tc_status) {
+        MVTB_CUDA(cudaMalloc((void**)&p->tc_status, sizeof(int)));
+        MVTB_CUDA(cudaMemset(p->tc_status, 0, sizeof(int)));
+    }
+    *out = p->tc_tab_fwd[slot];
+    return MVTB_OK;
+}
+#endif
 
 // One period of the fused kernel's work queue (bandlimited_sp.cuh): the A inverse tiles of a sample at times
 // 0 .. A-1, merged with the B select tiles of earlier samples at times lag + spread * j / B after their own sample's
@@ -797,9 +871,57 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         const int nv = n_volumes - v0 < chunk ? n_volumes - v0 : chunk;
         cf* Y = p->bl_ws;
         cf* G = Y + (size_t)chunk * NF * g.NC;
+        bool tc_fwd = false;
+#ifndef MVTB_EMU
+        const int tcN = (2 * NF + 15) / 16 * 16;
+        const size_t smem_tc = (((size_t)2 * g.H * tcN * sizeof(float) + 1023) & ~(size_t)1023) + (size_t)kTcRawStages * kTcRows * 128 * sizeof(float);
+        tc_fwd = p->opt_tc && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
+                 smem_tc <= (size_t)200 * 1024 && g.NC * (long long)g.H < 0x7fffffffLL;
+#endif
         {
-            ProfScope prof(p, MVTB_K_BL_FWD_H, stream);
+            ProfScope prof(p, tc_fwd ? MVTB_K_BL_FWD_TC : MVTB_K_BL_FWD_H, stream);
             const int ncb1 = (int)((g.NC + kColThreads - 1) / kColThreads);
+#ifndef MVTB_EMU
+            if (tc_fwd) {
+                // pruned DFT along H as a 3xTF32 GEMM on the tensor cores (bandlimited_tc.cuh)
+                TcFwdArgs ta;
+                CUtensorMap tmap;
+                int rcm = tc_make_tmap(&tmap, in + (size_t)v0 * p->vol_real, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, kTcRows);
+                if (rcm != MVTB_OK) return rcm;
+                ta.x = in + (size_t)v0 * p->vol_real;
+                ta.Y = Y;
+                int rct = tc_fwd_table(p, NF, tcN, &ta.tab);
+                if (rct != MVTB_OK) return rct;
+                ta.H = g.H; ta.NC = (int)g.NC; ta.NF = NF; ta.N = tcN;
+                ta.tiles_per_vol = (int)((g.NC + 127) / 128);
+                ta.n_tiles = ta.tiles_per_vol * nv;
+                ta.status = p->tc_status;
+                ta.prof = nullptr;
+                if (getenv("MVTB_TC_PROF")) {                  // measurements: waits and an event timeline of CTA 0, printed at the next call
+                    static long long* dprof = nullptr;
+                    const size_t np = 256 + 32 * 64;
+                    if (!dprof) { MVTB_CUDA(cudaMalloc((void**)&dprof, np * sizeof(long long))); }
+                    else {
+                        std::vector<long long> h(np);
+                        MVTB_CUDA(cudaMemcpy(h.data(), dprof, np * sizeof(long long), cudaMemcpyDeviceToHost));
+                        fprintf(stderr, "k_bl_fwd_tc CTA 0: total %lld cycles; waits by warp (codes 1..7):", h[0]);
+                        for (int w = 0; w < 27; ++w) { fprintf(stderr, "\n  warp %2d:", w); for (int c = 1; c < 8; ++c) fprintf(stderr, " %10lld", h[w * 8 + c]); }
+                        fprintf(stderr, "\nTRACE");
+                        for (int w = 0; w < 27; ++w)
+                            for (int i = 0; i < 64; ++i) {
+                                const long long e = h[256 + w * 64 + i];
+                                if (e) fprintf(stderr, "\nT %d %d %d %lld", w, (int)(e >> 56), (int)((e >> 40) & 0xffff), e & 0xffffffffffLL);
+                            }
+                        fprintf(stderr, "\nENDTRACE\n");
+                    }
+                    MVTB_CUDA(cudaMemset(dprof, 0, np * sizeof(long long)));
+                    ta.prof = dprof;
+                }
+                const unsigned grid = (unsigned)(ta.n_tiles < p->num_sms ? ta.n_tiles : p->num_sms);
+                if (p->tc_tma) MVTB_LAUNCH(k_bl_fwd_tc<true>, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
+                else MVTB_LAUNCH(k_bl_fwd_tc<false>, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
+            } else
+#endif
             if (quad && NF <= 16 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && p->opt_async) {
                 // cp.async staging ring: bytes in flight no longer limited by registers
                 const size_t smem_a = smem_h + sizeof(float) * kBlStages * 1024;
@@ -931,6 +1053,8 @@ int configure_bl_kernels(const mvtb_plan* p) {
     if ((rc = bl_configure_nf<26>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_configure_nf<32>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_mid, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_tc<true>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_tc<false>, optin)) != MVTB_OK) return rc;
 #endif
     (void)p;
     return MVTB_OK;

@@ -180,6 +180,12 @@ struct mvtb_plan {
     int is_spread_pct;                    // ... and are spread over this share of a period
     int is_store;                         // 0 streaming, 1 write-back, 2 write-back + L2 evict_last
     unsigned* is_sync;                    // queue head + per-sample completion counters
+    // tensor-core H-axis kernels (bandlimited_tc.cuh): operand tables per NF (built on first use), failure flag
+    int opt_tc;                           // 1: use them when the shape allows (MVTB_TC=1 or MVTB_PATH_BL_TC; off by default: see DESIGN 3.5)
+    int tc_tma;                           // 1: the forward kernel stages x with TMA tensor-map copies (MVTB_TC_TMA=1); 0: coalesced LDG
+    float* tc_tab_fwd[8];                 // by NF slot: [2][H * N] forward table (hi, lo)
+    float* tc_tab_inv[8];                 // by NF slot: inverse table
+    int* tc_status;                       // device int: 0, or the code of the bounded wait that expired
     // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
     void* stage_h[MVTB_STAGE_SLOTS];
     void* stage_d[MVTB_STAGE_SLOTS];
