@@ -116,13 +116,16 @@ int mvtb_salt_pepper_f32(const float* in, float* out, size_t n_per_sample, int n
                          const float* u, uint64_t seed, uint64_t offset, float p,
                          const float* minmax, void* stream);
 
-/* In-place salt-and-pepper whose cost is proportional to p: instead of one uniform per voxel, each block of
- * MVTB_SP_BLOCK consecutive voxels of a sample is walked from hit to hit with geometric gaps drawn from
- * Philox4x32-10 by inverse CDF against the integer table of mvtb_sparse_table (exact integer compares), plus
- * one random bit for salt vs pepper.  The voxels hit are i.i.d. Bernoulli(p) exactly as with `u <= p`, and
- * half of them get min/2, half max/2 (F:478-479).  Deterministic in (seed, offset, p); a different random
- * field than mvtb_salt_pepper_f32's.  table_dev: device scratch of MVTB_SP_BLOCK uint32 owned by the caller. */
+/* In-place salt-and-pepper whose cost is proportional to p: instead of one uniform per voxel, every span of
+ * MVTB_SP_SPAN consecutive voxels of a sample is walked from hit to hit by one warp, with geometric gaps drawn from
+ * Philox4x32-10 by inverse CDF against the integer table of mvtb_sparse_table (exact integer compares), plus one random
+ * bit per hit for salt vs pepper.  The voxels hit are i.i.d. Bernoulli(p) exactly as with `u <= p`, and half of them get
+ * min/2, half max/2 (F:478-479).  Deterministic in (seed, offset, p); a different random field than
+ * mvtb_salt_pepper_f32's.  Span s of sample i uses the Philox counters (offset + i * ceil(n_per_sample / MVTB_SP_SPAN)
+ * + s, ...): advance `offset` by at least n_samples * ceil(n_per_sample / MVTB_SP_SPAN) between calls.
+ * table_dev: device scratch of MVTB_SP_BLOCK uint32 owned by the caller. */
 #define MVTB_SP_BLOCK 256
+#define MVTB_SP_SPAN 8192
 int mvtb_salt_pepper_sparse_f32(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset,
                                 float p, const float* minmax, unsigned* table_dev, void* stream);
 /* T[k] = floor(2^32 (1 - (1-p)^(k+1))), k < MVTB_SP_BLOCK (host memory) */

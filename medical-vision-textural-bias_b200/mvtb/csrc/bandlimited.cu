@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "philox.cuh"
+#include "sp_sampler.cuh"
 #include "pointwise.cuh"
 #include "tc_common.cuh"
 
@@ -796,7 +797,10 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     const int vps = vols_per_sample;
     bool fuse = sp != nullptr && p->opt_fusesp && sp->p > 0.f && minmax_out != nullptr && quad && CPT == 2 && (g.NC % 2) == 0 &&
                 g.NC * (long long)g.H < 0x7fffffffLL && (((uintptr_t)out) & 7) == 0 && g.H / 4 - 1 >= 1 &&
-                vps >= 1 && vps <= kBlChunk && n_volumes % vps == 0;
+                vps >= 1 && vps <= kBlChunk && n_volumes % vps == 0 &&
+                // the select pass must find its sample in L2: beyond ~1.5 samples of 36 MB the lines are gone (tools/l2probe.cu)
+                // and the separate pass is faster (4-channel BraTS samples of 143 MB: 9.4 k vs 8.9 k samples/s)
+                (size_t)vps * p->vol_real * sizeof(float) <= ((size_t)p->is_max_sample_mb << 20);
     IsArgs ia;
     memset(&ia, 0, sizeof(ia));
     std::vector<unsigned> pattern;
@@ -813,8 +817,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         ia.ncb2 = (int)((g.NC / 2 + kColThreads - 1) / kColThreads);
         ia.A = vps * ia.ncb2 * HS;
         ia.n_per_sample = (unsigned long long)vps * p->vol_real;
-        const unsigned long long bps = (ia.n_per_sample + MVTB_SP_BLOCK - 1) / MVTB_SP_BLOCK;
-        const unsigned long long B = (bps + 255) / 256;
+        const unsigned long long bps = (ia.n_per_sample + MVTB_SP_SPAN - 1) / MVTB_SP_SPAN;   // spans per sample
+        const unsigned long long B = (bps + 8 * kIsSpansPerWarp - 1) / (8 * kIsSpansPerWarp);       // select tiles: 8 warps x kIsSpansPerWarp spans
         if (bps > 0x7fffffffull || B >= (1ull << 28) || (unsigned long long)ia.A >= (1ull << 28)) fuse = false;
         else {
             ia.bps = (unsigned)bps;
@@ -822,12 +826,12 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             const int spread = (int)((long long)ia.A * p->is_spread_pct / 100);
             is_build_pattern(ia.A, (int)B, lag, spread, pattern, &max_back);
             ia.period = (int)pattern.size();
-            ia.list_cap = sp->p <= 0.08f ? 40 : (sp->p <= 0.16f ? 64 : 112);
             const double l2q = log2(1.0 - (double)sp->p);
             ia.inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
             ia.seed = sp->seed;
             ia.offset = sp->offset;
             ia.minmax = minmax_out;
+            ia.debug = getenv("MVTB_IS_DEBUG") ? atoi(getenv("MVTB_IS_DEBUG")) : 0;
         }
     }
     if (fuse) {
@@ -874,9 +878,17 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         bool tc_fwd = false;
 #ifndef MVTB_EMU
         const int tcN = (2 * NF + 15) / 16 * 16;
-        const size_t smem_tc = (((size_t)2 * g.H * tcN * sizeof(float) + 1023) & ~(size_t)1023) + (size_t)kTcRawStages * kTcRows * 128 * sizeof(float);
+        // TMA boxes: k stages of 16 rows per copy, k the largest divisor of H / 16 with at most 64 rows; ring as deep as
+        // ~128 KB (and the table) allow, at most kTcRawStages stages
+        int tc_bs = 1;
+        for (int k = 1; k <= 4; ++k)
+            if ((g.H / kTcRows) % k == 0) tc_bs = k;
+        const size_t tc_tab = ((size_t)2 * g.H * tcN * sizeof(float) + 1023) & ~(size_t)1023;
+        int tc_ring = (int)(((size_t)200 * 1024 - tc_tab) / ((size_t)tc_bs * kTcRows * 128 * sizeof(float)));
+        if (tc_ring * tc_bs > kTcRawStages) tc_ring = kTcRawStages / tc_bs;
+        const size_t smem_tc = tc_tab + (size_t)tc_ring * tc_bs * kTcRows * 128 * sizeof(float);
         tc_fwd = p->opt_tc && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
-                 smem_tc <= (size_t)200 * 1024 && g.NC * (long long)g.H < 0x7fffffffLL;
+                 tc_ring >= 2 && g.NC * (long long)g.H < 0x7fffffffLL;
 #endif
         {
             ProfScope prof(p, tc_fwd ? MVTB_K_BL_FWD_TC : MVTB_K_BL_FWD_H, stream);
@@ -886,7 +898,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 // pruned DFT along H as a 3xTF32 GEMM on the tensor cores (bandlimited_tc.cuh)
                 TcFwdArgs ta;
                 CUtensorMap tmap;
-                int rcm = tc_make_tmap(&tmap, in + (size_t)v0 * p->vol_real, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, kTcRows);
+                int rcm = tc_make_tmap(&tmap, in + (size_t)v0 * p->vol_real, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, tc_bs * kTcRows);
                 if (rcm != MVTB_OK) return rcm;
                 ta.x = in + (size_t)v0 * p->vol_real;
                 ta.Y = Y;
@@ -895,6 +907,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 ta.H = g.H; ta.NC = (int)g.NC; ta.NF = NF; ta.N = tcN;
                 ta.tiles_per_vol = (int)((g.NC + 127) / 128);
                 ta.n_tiles = ta.tiles_per_vol * nv;
+                ta.box_stages = tc_bs;
+                ta.ring_boxes = tc_ring;
                 ta.status = p->tc_status;
                 ta.prof = nullptr;
                 if (getenv("MVTB_TC_PROF")) {                  // measurements: waits and an event timeline of CTA 0, printed at the next call
@@ -966,8 +980,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             ia.s_base = v0 / vps;
             ia.total = (unsigned)((ia.nsamp + max_back) * ia.period);
             MVTB_CUDA(cudaMemsetAsync(ia.sync, 0, sizeof(unsigned) * (size_t)(1 + ia.nsamp), (cudaStream_t)stream));
-            const size_t smem_is = smem_hi + sizeof(unsigned) * MVTB_SP_BLOCK + sizeof(int) * 256 +
-                                   sizeof(unsigned short) * 256 * (size_t)ia.list_cap;
+            const size_t smem_is = smem_hi + sizeof(unsigned) * MVTB_SP_BLOCK;
             unsigned grid = (unsigned)(p->num_sms * 2);
             if (grid > ia.total) grid = ia.total;
             float* o = out + (size_t)v0 * p->vol_real;

@@ -8,9 +8,9 @@
 //   inverse tile  I(s, j): 512 columns x one part of the H range (k_bl_inv_h4v's arithmetic, bl_inv_h4v_cols) of one
 //                          volume of sample s; output rows leave as plain write-back stores (they stay in L2), the
 //                          tile's (min, max) go to the sample's atomics, then a release increment of done[s];
-//   select tile   S(s, j): 256 blocks of 256 voxels of sample s walked by the geometric-gap sampler
-//                          (k_salt_pepper_sparse's arithmetic and Philox counters: bit-identical output), after an
-//                          acquire read of done[s] shows every inverse tile of the sample finished.
+//   select tile   S(s, j): 8 spans of 8192 voxels of sample s, one warp each, walked by the geometric-gap sampler
+//                          (sp_sampler.cuh: k_salt_pepper_sparse's arithmetic and Philox counters, bit-identical
+//                          output), after an acquire read of done[s] shows every inverse tile of the sample finished.
 //
 // The queue is a periodic sequence built on the host (one period = the inverse tiles of one sample merged with the
 // select tiles of earlier samples, `lag` inverse tiles behind and spread over the period), so that by the time a
@@ -21,6 +21,7 @@
 #pragma once
 
 #define MVTB_IS_SELECT 0x80000000u
+static const int kIsSpansPerWarp = 1;    // spans a warp of a select tile walks at a time (4 interleaved chains measured slower than 1: 14.5 vs 13.4 us)
 
 struct IsArgs {
     unsigned* sync;              // [0] queue head, [1 + s] finished inverse tiles of sample s; zeroed before the launch
@@ -35,9 +36,9 @@ struct IsArgs {
     float inv_log2q;
     unsigned long long seed, offset;
     unsigned long long n_per_sample;
-    unsigned bps;                // 256-voxel blocks per sample
-    int list_cap;                // hits listed per thread before it stores directly
+    unsigned bps;                // spans of MVTB_SP_SPAN voxels per sample
     float* minmax;               // 2 floats per sample of the call
+    int debug;                   // measurements: 1 = select tiles do no work, 2 = ... and do not wait, 4 = inverse tiles skip the fences
 };
 
 #ifdef MVTB_EMU
@@ -67,8 +68,6 @@ k_bl_inv_sp(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, const B
     float* sc = (float*)smem_raw;                                   // (cos, sin) rows 0 .. H/2 of the H axis
     cf* seh = (cf*)(sc + (H2 + 1) * NT);                            // plane-wave phases along H of the cached volume
     unsigned* sT = (unsigned*)(seh + MVTB_BL_MAX_PW * (H2 + 1));    // sampler table
-    int* sn = (int*)(sT + MVTB_SP_BLOCK);                           // hits listed per thread
-    unsigned short* sl = (unsigned short*)(sn + 256);               // [256][list_cap]: position | coin << 8
     __shared__ unsigned s_item;
     const int tid = threadIdx.x;
     bl_load_table<NF>(sc, g.tabC[2], g.tabS[2], H, tid, blockDim.x);
@@ -119,72 +118,25 @@ k_bl_inv_sp(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, const B
             float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
             bl_inv_h4v_cols<NF, STORE>(sc, seh, Y + (size_t)vol * NF * NC + col, out + (size_t)vol * H * NC + col, g, bv,
                                        col, ok, q0, q1, part == a.HS - 1, pol, lo, hi);
-            is_fence();                                             // this thread's rows are visible device-wide ...
+            if (!(a.debug & 4)) is_fence();                         // this thread's rows are visible device-wide ...
             bl_block_minmax(lo, hi, a.minmax + 2 * (size_t)(a.s_base + s));
             if (tid == 0) {                                         // ... before the tile counts as finished
                 is_fence();
                 atomicAdd(a.sync + 1 + s, 1u);
             }
         } else {
-            // ---------------------------------------------------------------- select tile
-            if (tid == 0)
+            // ---------------------------------------------------------------- select tile: 8 warps x kIsSpansPerWarp spans
+            if (tid == 0 && !(a.debug & 2))
                 while (ld_acquire_u32(a.sync + 1 + s) < (unsigned)a.A) is_sleep();
             __syncthreads();
+            if (a.debug & 1) continue;
             const float* mm = a.minmax + 2 * (size_t)(a.s_base + s);
             const float lo = 0.5f * ld_l2_f32(mm), hi = 0.5f * ld_l2_f32(mm + 1);
-            float* xs = out + (size_t)s * a.n_per_sample;
-            const unsigned b = (unsigned)j * 256u + (unsigned)tid;  // this thread's block within the sample
-            unsigned short* my = sl + (size_t)tid * a.list_cap;
-            int nlist = 0;
-            if (b < a.bps) {
-                const size_t j0 = (size_t)b * MVTB_SP_BLOCK;
-                const int len = (int)((a.n_per_sample - j0) < (unsigned long long)MVTB_SP_BLOCK ? (a.n_per_sample - j0)
-                                                                                                : (unsigned long long)MVTB_SP_BLOCK);
-                const unsigned long long gb = a.offset + (unsigned long long)(a.s_base + s) * a.bps + b;
-                int pos = -1;
-                unsigned call = 0;
-                bool done = false;
-                while (!done) {
-                    const uint4 rr = Philox::run(make_uint4((unsigned)gb, (unsigned)(gb >> 32), call, 0x5350u), key);
-                    const unsigned words[2] = {rr.x, rr.y};
-                    MVTB_UNROLL
-                    for (int w2 = 0; w2 < 2; ++w2) {
-                        const unsigned w = words[w2];
-                        const float v = (float)(~w) * 2.3283064365386963e-10f;
-#ifdef MVTB_EMU
-                        const float kf = log2f(v) * a.inv_log2q;
-#else
-                        const float kf = __log2f(v) * a.inv_log2q;
-#endif
-                        int lo_k = (int)fminf(fmaxf(kf, 0.f), (float)MVTB_SP_BLOCK);
-                        while (lo_k > 0 && w < sT[lo_k - 1]) --lo_k;
-                        while (lo_k < MVTB_SP_BLOCK && w >= sT[lo_k]) ++lo_k;
-                        pos += lo_k + 1;
-                        if (!done && pos < len) {
-                            const unsigned coin = (rr.z >> w2) & 1u;
-                            if (nlist < a.list_cap) my[nlist++] = (unsigned short)(pos | (coin << 8));
-                            else xs[j0 + pos] = coin ? hi : lo;
-                        } else {
-                            done = true;
-                        }
-                    }
-                    ++call;
-                }
-            }
-            sn[tid] = nlist;
-            __syncwarp();
-            // the warp writes the lists out block by block: one store instruction carries the hits of one 1 KB block
-            const int lane = tid & 31, w0 = tid & ~31;
-            float* xw = xs + ((size_t)j * 256 + w0) * MVTB_SP_BLOCK;
-            for (int k = 0; k < 32; ++k) {
-                const int nk = sn[w0 + k];
-                float* xk = xw + (size_t)k * MVTB_SP_BLOCK;
-                const unsigned short* lk = sl + (size_t)(w0 + k) * a.list_cap;
-                for (int i = lane; i < nk; i += 32) {
-                    const unsigned en = lk[i];
-                    xk[en & 255u] = ((en >> 8) & 1u) ? hi : lo;
-                }
-            }
+            const unsigned span = ((unsigned)j * 8u + (unsigned)(tid >> 5)) * kIsSpansPerWarp;
+            if (span < a.bps)
+                sp_walk_spans<kIsSpansPerWarp>(out + (size_t)s * a.n_per_sample, a.n_per_sample, span, a.bps,
+                                               a.offset + (unsigned long long)(a.s_base + s) * a.bps + span, key, sT, a.inv_log2q,
+                                               lo, hi, tid & 31);
         }
     }
 }

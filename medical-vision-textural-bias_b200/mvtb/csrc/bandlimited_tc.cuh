@@ -22,7 +22,7 @@
 // tc_common.cuh is included by bandlimited.cu before namespace mvtb opens
 
 static const int kTcRows = 16;          // rows of x per stage (two MMA K-steps of 8)
-static const int kTcRawStages = 8;      // raw shared-memory stages (8 KB each)
+static const int kTcRawStages = 16;     // raw shared-memory stages (8 KB each), at most; filled box by box (k stages per TMA copy)
 static const int kTcASlotsMax = 8;      // A-operand slots in TMEM (32 columns each: 16 hi + 16 lo)
 static const int kTcConvGroups = 4;     // converter groups of 4 warps (one per TMEM lane quarter); group g takes stages g, g+4, ...
 static const int kTcIssuers = 6;        // MMA-issuing warps: (3xTF32 term, K-step of the stage), each with its own accumulator
@@ -35,6 +35,8 @@ struct TcFwdArgs {
     const float* tab;        // [2][H * N]: B operand hi, lo in tc::op_offset layout; row 2f = cos, 2f+1 = -sin, k = h
     int H, NC, NF, N;        // N = 2 NF rounded up to a multiple of 16
     int n_tiles, tiles_per_vol;
+    int box_stages;          // TMA path: stages (of 16 rows) per tensor-map box
+    int ring_boxes;          // TMA path: boxes in the raw shared-memory ring
     int* status;
     long long* prof;         // null, or [32 warps][8] wait cycles of CTA 0 (+ [0][0] = total cycles)
 };
@@ -138,22 +140,33 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
         // ------------------------------------------------------------ producer: one TMA box (16 rows x 128 columns) per stage
         unsigned it = 0;
         if (!TMA_LOAD) it = 0xffffffffu;
+        // One copy brings `box_stages` stages (measured: a copy costs the issuing thread ~550 cycles and lands ~2.9 k
+        // cycles later, so 8 KB copies eight deep delivered 22 B/clk per SM, just under the HBM share of an SM;
+        // 24 KB boxes, five deep, keep 120 KB in flight).  Stage s of the ring is `full` when its box has landed; the
+        // box is refilled when all its stages have been released.
+        const int bs = a.box_stages, ring = a.ring_boxes * bs;            // stages in the ring
+        const int n_box = n_stage / bs;
+        unsigned ib = 0;                                                  // box counter
         for (int tile = blockIdx.x; TMA_LOAD && tile < a.n_tiles && !*abortp; tile += gridDim.x) {
             const int vol = tile / a.tiles_per_vol, c0 = (tile - vol * a.tiles_per_vol) * 128;
             bool ok = true;
-            for (int st = 0; st < n_stage; ++st, ++it) {
-                const int s = it % kTcRawStages;
-                if (!tc_wait(&bars.raw_empty[s], ((it / kTcRawStages) & 1) ^ 1, abortp, a.status, 1, a.prof)) { ok = false; break; }
+            for (int b = 0; b < n_box; ++b, ++ib) {
+                const int rb = (int)(ib % (unsigned)a.ring_boxes);        // ring slot of this box
+                const uint32_t ph = ((ib / (unsigned)a.ring_boxes) & 1u) ^ 1u;
+                for (int k = 0; k < bs && ok; ++k)                        // every stage of the slot must have been released
+                    if (!tc_wait(&bars.raw_empty[rb * bs + k], ph, abortp, a.status, 1, a.prof)) ok = false;
+                if (!ok) break;
                 if (tc::elect_one()) {
-                    const uint32_t full = tc::smem_u32(&bars.raw_full[s]);
-                    tc::mbar_arrive_expect_tx(full, kTcRows * 128 * 4);       // the whole box, columns past NC arrive as zeros
-                    tc::tma_load_2d(tc::smem_u32(raw + (size_t)s * kTcRows * 128), &tmap, c0, vol * H + st * kTcRows, full);
+                    const uint32_t full = tc::smem_u32(&bars.raw_full[rb]);
+                    tc::mbar_arrive_expect_tx(full, (uint32_t)bs * kTcRows * 128 * 4);  // the whole box, columns past NC arrive as zeros
+                    tc::tma_load_2d(tc::smem_u32(raw + (size_t)rb * bs * kTcRows * 128), &tmap, c0, vol * H + b * bs * kTcRows, full);
                 }
                 __syncwarp();
-                TC_TRACE(6, it);
+                TC_TRACE(6, ib);
             }
             if (!ok) break;
         }
+        (void)ring;
     } else if (warp < kTcWarpEpi0) {
         // ------------------------------------------------------------ MMA issuers
         const int iss = warp - kTcWarpIss0, term = iss >> 1, ks = iss & 1;   // term 0 = hi*hi, 1 = lo*hi, 2 = hi*lo
@@ -235,8 +248,12 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
                 bool ok = true;
                 for (int st = 0; st < n_stage; ++st, ++it) {
                     if ((int)(it % kTcConvGroups) != grp) continue;
-                    const int s = it % kTcRawStages, sl = it & (a_slots - 1);
-                    if (!tc_wait(&bars.raw_full[s], (it / kTcRawStages) & 1, abortp, a.status, 5, a.prof)) { ok = false; break; }
+                    const int sl = it & (a_slots - 1);
+                    const unsigned ibx = it / (unsigned)a.box_stages;                      // box counter (n_stage % box_stages == 0)
+                    const int kb = (int)(it - ibx * (unsigned)a.box_stages);               // stage within the box
+                    const int rb = (int)(ibx % (unsigned)a.ring_boxes);
+                    const int s = rb * a.box_stages + kb;
+                    if (!tc_wait(&bars.raw_full[rb], (ibx / (unsigned)a.ring_boxes) & 1u, abortp, a.status, 5, a.prof)) { ok = false; break; }
                     TC_TRACE(3, it);
                     const float* rp = raw + (size_t)s * kTcRows * 128 + m;
                     float v[kTcRows];

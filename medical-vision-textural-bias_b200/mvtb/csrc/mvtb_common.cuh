@@ -179,6 +179,7 @@ struct mvtb_plan {
     int is_lag;                           // select tiles trail their sample's inverse tiles by this many tiles (-1: one wave of CTAs)
     int is_spread_pct;                    // ... and are spread over this share of a period
     int is_store;                         // 0 streaming, 1 write-back, 2 write-back + L2 evict_last
+    int is_max_sample_mb;                 // samples larger than this take the separate select pass (their lines leave L2 first)
     unsigned* is_sync;                    // queue head + per-sample completion counters
     // tensor-core H-axis kernels (bandlimited_tc.cuh): operand tables per NF (built on first use), failure flag
     int opt_tc;                           // 1: use them when the shape allows (MVTB_TC=1 or MVTB_PATH_BL_TC; off by default: see DESIGN 3.5)

@@ -139,10 +139,11 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->opt_tc = getenv("MVTB_TC") ? atoi(getenv("MVTB_TC")) : 0;
     p->tc_tma = getenv("MVTB_TC_TMA") ? atoi(getenv("MVTB_TC_TMA")) : 0;
     p->is_chunk = getenv("MVTB_IS_CHUNK") ? atoi(getenv("MVTB_IS_CHUNK")) : 0;
-    p->is_hs = getenv("MVTB_IS_HS") ? atoi(getenv("MVTB_IS_HS")) : 4;
+    p->is_hs = getenv("MVTB_IS_HS") ? atoi(getenv("MVTB_IS_HS")) : 2;
     p->is_lag = getenv("MVTB_IS_LAG") ? atoi(getenv("MVTB_IS_LAG")) : -1;
     p->is_spread_pct = getenv("MVTB_IS_SPREAD") ? atoi(getenv("MVTB_IS_SPREAD")) : 100;
-    p->is_store = getenv("MVTB_IS_STORE") ? atoi(getenv("MVTB_IS_STORE")) : 1;
+    p->is_max_sample_mb = getenv("MVTB_IS_MAX_MB") ? atoi(getenv("MVTB_IS_MAX_MB")) : 48;
+    p->is_store = getenv("MVTB_IS_STORE") ? atoi(getenv("MVTB_IS_STORE")) : 2;
     p->chunk = chunk_volumes;
     p->device = device;
     p->num_sms = prop.multiProcessorCount;

@@ -7,6 +7,7 @@
 
 #include "mvtb_common.cuh"
 #include "philox.cuh"
+#include "sp_sampler.cuh"
 
 namespace mvtb {
 
@@ -218,102 +219,27 @@ k_salt_pepper_vec(const float* __restrict__ in, float* __restrict__ out, unsigne
 
 
 // ------------------------------------------------------------------ sparse salt and pepper (in place)
-// The dense kernels spend ~17 instructions per voxel on Philox although only a fraction p of the voxels
-// changes.  Here each thread owns a block of MVTB_SP_BLOCK consecutive voxels of one sample and walks from
-// hit to hit: the number of untouched voxels before the next hit is geometric, P(gap >= k) = (1-p)^k, drawn
-// by inverse CDF from one 32-bit Philox word against the integer table T[k] = floor(2^32 (1 - (1-p)^(k+1)))
-// (binary search, exact integer compares); one more random bit picks salt or pepper (the reference's
-// u <= p/2 | u <= p is a fair coin).  The voxels hit are i.i.d. Bernoulli(p), as with one uniform per voxel,
-// at a cost proportional to p.  Counter layout: (offset + global block id, call index, tag 0x5350).
-// Two phases per warp.  (1) Every lane walks its own block and only *lists* its hits in shared memory.  (2) The
-// warp writes the lists out block by block: one store instruction carries all hits of one 1 KB block.  Storing
-// from inside the walk (lane i at its own block, 32 blocks = 32 KB apart per instruction, a block's dozen hits
-// spread over the thread's lifetime) made every 4-byte read-modify-write of a sector its own DRAM page visit:
-// 1.6 TB/s, 15 us per volume, twice the dense kernel.
-// kSpNB consecutive blocks per thread are walked in one flat loop (one Philox call per trip, whichever block the
-// thread is in), which keeps a warp converged longer; measured on B200 at p = 0.05: 6.7 us/volume with 1 block per
-// thread, 7.2 with 2, 7.5 with 4.  Evaluating four Philox calls (eight gaps) per trip with a branch-free table
-// lookup, so that their latencies overlap, changed nothing (6.7): at 3.6 TB/s of 32-byte sector read-modify-write
-// (the same 24 MB per volume the dense kernel moves at 3.0 TB/s) the kernel sits on the memory system's rate for
-// partial-sector writes, not on instructions.
-static_assert(MVTB_SP_BLOCK == 256, "the hit lists pack the position into 8 bits");
-static const int kSpNB = 1;              // consecutive blocks per thread
-// hits listed per thread, the rest is stored directly: 40 for p <= 0.08 (mean 12.8 per block at p = 0.05), 64 up to
-// 0.16, 112 beyond -- a longer list costs occupancy, a shorter one scattered stores (p = 0.15: 9.35 -> 8.74 us/volume)
-static const int kSpThreadsSparse = 128;
+// One warp per span of MVTB_SP_SPAN voxels (sp_sampler.cuh).  grid = (spans per sample / warps per CTA, samples).
+static const int kSpThreadsSparse = 256;
 
-template <int kSpListCap>
 __global__ void __launch_bounds__(kSpThreadsSparse)
-k_salt_pepper_sparse(float* __restrict__ x, size_t n_per_sample, unsigned blocks_per_sample,
+k_salt_pepper_sparse(float* __restrict__ x, unsigned long long n_per_sample, unsigned spans_per_sample,
                      const unsigned* __restrict__ table, float inv_log2q, uint64_t seed, uint64_t offset,
                      const float* __restrict__ mm) {
     __shared__ unsigned sT[MVTB_SP_BLOCK];
-    __shared__ unsigned short sl[kSpThreadsSparse][kSpListCap];    // position (8 bits) | coin << 8 | block in thread << 9
-    __shared__ int sn[kSpThreadsSparse];
+    __shared__ unsigned short s_stage[kSpThreadsSparse / 32][kSpStageIters * 96];
     for (int e = threadIdx.x; e < MVTB_SP_BLOCK; e += blockDim.x) sT[e] = __ldg(table + e);
     __syncthreads();
     const unsigned smp = blockIdx.y;
     const float lo = 0.5f * __ldg(mm + 2 * smp), hi = 0.5f * __ldg(mm + 2 * smp + 1);
-    float* xs = x + (size_t)smp * n_per_sample;
-    const unsigned b0 = (blockIdx.x * blockDim.x + threadIdx.x) * kSpNB;     // this thread's first block in the sample
+    const unsigned span = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (span >= spans_per_sample) return;                      // whole warps leave together
     uint2 key;
     key.x = (unsigned)seed;
     key.y = (unsigned)(seed >> 32);
-    int nlist = 0, blk = 0, pos = -1;
-    unsigned call = 0;
-    bool live = b0 < blocks_per_sample;
-    while (live) {
-        const unsigned b = b0 + blk;
-        const size_t j0 = (size_t)b * MVTB_SP_BLOCK;
-        const int len = (int)((n_per_sample - j0) < (size_t)MVTB_SP_BLOCK ? (n_per_sample - j0) : (size_t)MVTB_SP_BLOCK);
-        const uint64_t gb = offset + (uint64_t)smp * blocks_per_sample + b;
-        const uint4 r = Philox::run(make_uint4((unsigned)gb, (unsigned)(gb >> 32), call, 0x5350u), key);
-        const unsigned words[2] = {r.x, r.y};
-        bool done = false;
-        MVTB_UNROLL
-        for (int t = 0; t < 2; ++t) {
-            const unsigned w = words[t];
-            // gap = smallest k with w < T[k]; T is non-decreasing; k = MVTB_SP_BLOCK means "beyond this block".
-            // T[k] ~ 2^32 (1 - q^(k+1)), so k ~ floor(log2(1 - w / 2^32) / log2 q): one MUFU guess, then the exact
-            // integer table settles it (usually zero or one probe each way): the binary search's result, bit for bit.
-            const float v = (float)(~w) * 2.3283064365386963e-10f;          // 1 - w / 2^32 without cancellation
-#ifdef MVTB_EMU
-            const float kf = log2f(v) * inv_log2q;
-#else
-            const float kf = __log2f(v) * inv_log2q;
-#endif
-            int lo_k = (int)fminf(fmaxf(kf, 0.f), (float)MVTB_SP_BLOCK);    // NaN -> 0 (fmaxf) -> corrected below
-            while (lo_k > 0 && w < sT[lo_k - 1]) --lo_k;
-            while (lo_k < MVTB_SP_BLOCK && w >= sT[lo_k]) ++lo_k;
-            pos += lo_k + 1;
-            if (!done && pos < len) {
-                const unsigned coin = (r.z >> t) & 1u;
-                if (nlist < kSpListCap) sl[threadIdx.x][nlist++] = (unsigned short)(pos | (coin << 8) | (blk << 9));
-                else xs[j0 + pos] = coin ? hi : lo;
-            } else {
-                done = true;
-            }
-        }
-        ++call;
-        if (done) {                                  // next block of this thread
-            ++blk;
-            call = 0;
-            pos = -1;
-            live = blk < kSpNB && b0 + blk < blocks_per_sample;
-        }
-    }
-    sn[threadIdx.x] = nlist;
-    __syncwarp();
-    const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
-    float* xw = xs + (size_t)(blockIdx.x * blockDim.x + w0) * kSpNB * MVTB_SP_BLOCK;
-    for (int j = 0; j < 32; ++j) {
-        const int nj = sn[w0 + j];
-        float* xj = xw + (size_t)j * kSpNB * MVTB_SP_BLOCK;
-        for (int i = lane; i < nj; i += 32) {
-            const unsigned e = sl[w0 + j][i];
-            xj[(e >> 9) * MVTB_SP_BLOCK + (e & 255u)] = ((e >> 8) & 1u) ? hi : lo;
-        }
-    }
+    sp_walk_spans<1>(x + (size_t)smp * n_per_sample, n_per_sample, span, spans_per_sample,
+                     offset + (uint64_t)smp * spans_per_sample + span, key, sT, inv_log2q, lo, hi, threadIdx.x & 31,
+                     s_stage[threadIdx.x >> 5]);
 }
 
 // ------------------------------------------------------------------ wraparound fold (all axes even)
@@ -456,22 +382,14 @@ namespace mvtb {
 int sparse_sp_launch(float* x, size_t n_per_sample, int n_samples, uint64_t seed, uint64_t offset, float p,
                      const float* minmax, const unsigned* table_dev, void* stream) {
     if (p == 0.f || n_samples == 0 || n_per_sample == 0) return MVTB_OK;   // T = 0 everywhere: no voxel is ever selected
-    const size_t bps = (n_per_sample + MVTB_SP_BLOCK - 1) / MVTB_SP_BLOCK;
-    if (bps > 0x7fffffffull) { set_error("salt_pepper_sparse: sample too large"); return MVTB_EUNSUPPORTED; }
-    const unsigned per_cta = (unsigned)(kSpThreadsSparse * kSpNB);
-    const unsigned gx = (unsigned)((bps + per_cta - 1) / per_cta);
+    const size_t sps = (n_per_sample + MVTB_SP_SPAN - 1) / MVTB_SP_SPAN;
+    if (sps > 0x7fffffffull) { set_error("salt_pepper_sparse: sample too large"); return MVTB_EUNSUPPORTED; }
+    const unsigned per_cta = (unsigned)(kSpThreadsSparse / 32);
+    const unsigned gx = (unsigned)((sps + per_cta - 1) / per_cta);
     const double l2q = log2(1.0 - (double)p);          // -inf for p = 1: the guess is then 0 and the table decides
     const float inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
-#define MVTB_SPARSE_LAUNCH(CAP)                                                                                   \
-    do {                                                                                                          \
-        auto kern = k_salt_pepper_sparse<CAP>;                                                                    \
-        MVTB_LAUNCH(kern, dim3(gx, (unsigned)n_samples), dim3(kSpThreadsSparse), 0, stream, x, n_per_sample,      \
-                    (unsigned)bps, table_dev, inv_log2q, seed, offset, minmax);                                   \
-    } while (0)
-    if (p <= 0.08f) MVTB_SPARSE_LAUNCH(40);
-    else if (p <= 0.16f) MVTB_SPARSE_LAUNCH(64);
-    else MVTB_SPARSE_LAUNCH(112);
-#undef MVTB_SPARSE_LAUNCH
+    MVTB_LAUNCH(k_salt_pepper_sparse, dim3(gx, (unsigned)n_samples), dim3(kSpThreadsSparse), 0, stream, x,
+                (unsigned long long)n_per_sample, (unsigned)sps, table_dev, inv_log2q, seed, offset, minmax);
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;
 }

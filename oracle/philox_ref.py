@@ -70,30 +70,47 @@ def sparse_table(p):
     return out
 
 
+SP_SPAN = 8192
+SP_TAG = 0x5351
+
+
 def sparse_hits(n_per_sample, n_samples, seed, offset, p):
     """Positions (flat index into the whole buffer) and kinds (1 = salt/max, 0 = pepper/min) that
-    mvtb_salt_pepper_sparse_f32 touches.  Pure-Python loops: small cases only."""
+    mvtb_salt_pepper_sparse_f32 / mvtb_kspace_chain_sp_f32 touch (restates csrc/sp_sampler.cuh).
+
+    Each span of SP_SPAN voxels is one stream: iteration i, lane l (0..31) takes Philox words x, y, z of counter
+    (span id lo, span id hi, 32 i + l, SP_TAG); a word w gives k = #{T <= w}; k < 256: advance k + 1 and hit the voxel
+    reached, else advance 256 without a hit; coins are bits 0..2 of word w.  Words are consumed in (i, l, x|y|z)
+    order until the span is covered; hits past its end are dropped."""
     T = sparse_table(p).astype(np.uint64)
-    bps = (n_per_sample + SP_BLOCK - 1) // SP_BLOCK
+    sps = (n_per_sample + SP_SPAN - 1) // SP_SPAN
+    key1 = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
     pos_out, kind_out = [], []
-    key = np.array([[seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]], dtype=np.uint32)
+    lanes = np.arange(32, dtype=np.uint32)
     for s in range(n_samples):
-        for b in range(bps):
-            j0 = b * SP_BLOCK
-            length = min(SP_BLOCK, n_per_sample - j0)
-            gb = offset + s * bps + b
-            pos, call, done = -1, 0, False
-            while not done:
-                ctr = np.array([[gb & 0xFFFFFFFF, (gb >> 32) & 0xFFFFFFFF, call, 0x5350]], dtype=np.uint32)
-                r = philox4x32_10(ctr, key)[0]
-                for t in range(2):
-                    w = np.uint64(r[t])
-                    gap = int(np.searchsorted(T, w, side="right"))       # smallest k with w < T[k]
-                    pos += gap + 1
-                    if not done and pos < length:
-                        pos_out.append(s * n_per_sample + j0 + pos)
-                        kind_out.append((int(r[2]) >> t) & 1)
-                    else:
-                        done = True
-                call += 1
-    return np.array(pos_out, dtype=np.int64), np.array(kind_out, dtype=np.int64)
+        for sp in range(sps):
+            j0 = sp * SP_SPAN
+            length = min(SP_SPAN, n_per_sample - j0)
+            gs = offset + s * sps + sp
+            base, it = 0, 0
+            while base < length:
+                ctr = np.zeros((32, 4), dtype=np.uint32)
+                ctr[:, 0] = np.uint32(gs & 0xFFFFFFFF)
+                ctr[:, 1] = np.uint32((gs >> 32) & 0xFFFFFFFF)
+                ctr[:, 2] = np.uint32(it * 32) + lanes
+                ctr[:, 3] = np.uint32(SP_TAG)
+                r = philox4x32_10(ctr, np.broadcast_to(key1, (32, 2)))
+                w = r[:, :3].astype(np.uint64).reshape(-1)                    # (lane, word) order
+                k = np.searchsorted(T, w, side="right")                       # smallest k with w < T[k]; 256 if none
+                hit = k < SP_BLOCK
+                adv = np.where(hit, k + 1, SP_BLOCK)
+                pos = base + np.cumsum(adv) - 1
+                coin = ((r[:, 3][:, None] >> np.arange(3, dtype=np.uint32)[None, :]) & 1).reshape(-1)
+                sel = hit & (pos < length)
+                pos_out.append(s * n_per_sample + j0 + pos[sel])
+                kind_out.append(coin[sel].astype(np.int64))
+                base += int(adv.sum())
+                it += 1
+    if not pos_out:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    return np.concatenate(pos_out).astype(np.int64), np.concatenate(kind_out).astype(np.int64)

@@ -100,6 +100,13 @@ static inline T __shfl_xor_sync(unsigned, T v, int m, int width = 32) {
     return cuemu_shfl(v, cuemu::lane_id() ^ m);
 }
 template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
+    int l = cuemu::lane_id();
+    int s = l - (int)d;
+    if (s < 0 || (s / width) != (l / width)) s = l;
+    return cuemu_shfl(v, s);
+}
+template <typename T>
 static inline T __shfl_down_sync(unsigned, T v, unsigned d, int width = 32) {
     int l = cuemu::lane_id();
     int s = l + (int)d;

@@ -62,7 +62,7 @@ def test_fused_equals_two_calls(cuda_device, shape, vps, p):
     got, mm2 = Fn.kspace_chain_sp(x, 3, descs, p, seed=31, offset=12345, vols_per_sample=vps)
     torch.cuda.synchronize()
     kinds = _kinds(plan)
-    assert "k_bl_inv_sp" in kinds and "k_bl_inv_h" not in kinds
+    assert "k_bl_inv_sp" in kinds and "k_bl_inv_h" not in kinds        # (samples of these sizes fit in L2: fused)
     assert torch.equal(mm, mm2)
     assert torch.equal(got, want)
     assert not torch.equal(got, y3)

@@ -4,6 +4,6 @@ O=gpurun_out/c7; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_tc.py -x -q > $O/pytest_tc.log 2>&1; echo "rc=$?" >> $O/pytest_tc.log
 tail -5 $O/pytest_tc.log
 B="timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e"
-MVTB_TWO_CALLS=1 $B > $O/b_ldg.log 2>&1
-MVTB_TC_TMA=1 MVTB_TWO_CALLS=1 $B > $O/b_tma.log 2>&1
-MVTB_TC_PROF=1 MVTB_TWO_CALLS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/b_prof.log 2> $O/b_prof.err
+MVTB_TC=1 MVTB_TWO_CALLS=1 $B > $O/b_ldg.log 2>&1
+MVTB_TC=1 MVTB_TC_TMA=1 MVTB_TWO_CALLS=1 $B > $O/b_tma.log 2>&1
+MVTB_TC=1 MVTB_TC_TMA=1 MVTB_TC_PROF=1 MVTB_TWO_CALLS=1 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > $O/b_prof.log 2> $O/b_prof.err
