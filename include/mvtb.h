@@ -99,6 +99,18 @@ int mvtb_kspace_chain_sp_f32(mvtb_plan* plan, const float* in, float* out, int n
                              const mvtb_chain_desc* desc, int n_desc, float* minmax_out, int vols_per_sample,
                              float p, uint64_t seed, uint64_t offset, void* stream);
 
+/* The general form: optional intensity prologue map on the way in (pre_abt: device float[3 * n_volumes], one (a, b, t)
+ * per volume from mvtb_intensity_prologue_coeffs_f32, y = x != 0 ? a x + b : t; NULL = none), the chain, and an
+ * optional sparse salt-and-pepper pass on the way out (sp: NULL = none; then minmax_out may be NULL too).
+ * mvtb_kspace_chain_f32 / _sp_f32 are this call with the corresponding arguments NULL. */
+typedef struct mvtb_sp_params {
+    float p;
+    uint64_t seed, offset;
+} mvtb_sp_params;
+int mvtb_kspace_chain_ex_f32(mvtb_plan* plan, const float* in, float* out, int n_volumes,
+                             const mvtb_chain_desc* desc, int n_desc, const float* pre_abt,
+                             float* minmax_out, int vols_per_sample, const mvtb_sp_params* sp, void* stream);
+
 /* sum over the full (unshifted, unnormalised) spectrum of log(|k| + 1e-10) per volume, into
  * device double[n_volumes]; the caller divides by the volume size and multiplies by 2.5
  * (KSpaceSpikeNoise default intensity F:932-933, RandKSpaceSpikeNoise default range F:1127-1130). */
@@ -133,6 +145,34 @@ int mvtb_sparse_table(float p, unsigned* table_out);
 
 /* the uniforms mvtb_salt_pepper_f32 uses when u == NULL (for tests and for feeding the oracle) */
 int mvtb_philox_uniform_f32(float* out, size_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- intensity prologue: NormalizeIntensityd(nonzero=True, channel_wise=True) -> RandScaleIntensityd ->
+ * RandShiftIntensityd, the MONAI 0.5 transforms in front of the chain in every training script of the reference
+ * (10_scripts/127_.../stylized_gibbs12p5_spikes15_wrap0p5_sap0p05_FLAIR.py:134-136).  Per channel c with m = x != 0:
+ *   y = m ? ((x - mean(x[m])) / std(x[m])) * scale[c] + shift[c] : shift[c]     (population std; 1 if it is 0)
+ * mvtb_intensity_prologue_coeffs_f32: one read of the data -> stats_out[c] = (count, mean, std) (device double[3C],
+ *   nullable) and abt_out[c] = (a, b, t) with y = m ? a x + b : t (device float[3C], nullable).  scale / shift: device
+ *   float[C] (1 + factor and offset of the two random transforms; NULL = not applied).  scratch: device buffer of
+ *   mvtb_intensity_scratch_bytes(C) bytes.  Deterministic (fixed-order reduction in double).
+ * mvtb_intensity_affine_f32: the map on its own, in == out allowed.
+ * mvtb_kspace_chain_ex_f32 (below) applies the map while the chain reads the volume (one triple per volume). */
+size_t mvtb_intensity_scratch_bytes(int n_channels);
+int mvtb_intensity_prologue_coeffs_f32(const float* in, size_t n_per_channel, int n_channels, const float* scale,
+                                       const float* shift, double* stats_out, float* abt_out, void* scratch, void* stream);
+int mvtb_intensity_affine_f32(const float* in, float* out, size_t n_per_channel, int n_channels, const float* abt,
+                              void* stream);
+
+/* ---- Dice loss / metric reductions behind the hot path (MONAI 0.5 DiceLoss(sigmoid=True, squared_pred=True),
+ * Activations(sigmoid) -> AsDiscrete(0.5) -> DiceMetric; 10_scripts/127_.../...FLAIR.py:216, 266-283).
+ * mvtb_dice_sums_f32: one pass over x (logits if from_logits, else probabilities / binary predictions) and target,
+ *   n_vols = B*C volumes of n_per_vol voxels -> sums_out[6 v ..] = sum t p, sum p^2, sum t^2, sum t q, sum q, sum t
+ *   (p = sigmoid(x) or x, q = [p >= 0.5]) as device doubles; deterministic.  scratch: mvtb_dice_scratch_bytes(n_vols).
+ * mvtb_dice_grad_f32: grad_out_i = (coef[2v] t_i + coef[2v+1] p_i) * (from_logits ? p_i (1 - p_i) : 1). */
+size_t mvtb_dice_scratch_bytes(int n_vols);
+int mvtb_dice_sums_f32(const float* x, const float* target, size_t n_per_vol, int n_vols, int from_logits,
+                       double* sums_out, void* scratch, void* stream);
+int mvtb_dice_grad_f32(const float* x, const float* target, size_t n_per_vol, int n_vols, int from_logits,
+                       const float* coef, float* grad_out, void* stream);
 
 /* WrapArtifact (F:503-515) on (C,H,W,D) when H, W and D are all even: the image-domain fold
  * out = prod_axes (c0 + s c1 Roll_{N/2}) x, c0=(1+alpha)/2, c1=(1-alpha)/2, s=(-1)^(N/2)

@@ -32,6 +32,10 @@ class ChainDesc(C.Structure):
     ]
 
 
+class SpParams(C.Structure):
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
 class MvtbError(RuntimeError):
     def __init__(self, code, text):
         super().__init__(f"libmvtb error {code}: {text}")
@@ -48,6 +52,8 @@ _SYMBOLS = {
                                         C.c_void_p, C.c_int, C.c_void_p]),
     "mvtb_kspace_chain_sp_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ChainDesc), C.c_int,
                                            C.c_void_p, C.c_int, C.c_float, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mvtb_kspace_chain_ex_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(ChainDesc), C.c_int, C.c_void_p,
+                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_kspace_logabs_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_minmax_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "mvtb_salt_pepper_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
@@ -56,6 +62,13 @@ _SYMBOLS = {
                                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvtb_sparse_table": (C.c_int, [C.c_float, C.POINTER(C.c_uint32)]),
     "mvtb_philox_uniform_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "mvtb_intensity_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "mvtb_intensity_prologue_coeffs_f32": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                     C.c_void_p, C.c_void_p]),
+    "mvtb_intensity_affine_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
+    "mvtb_dice_scratch_bytes": (C.c_size_t, [C.c_int]),
+    "mvtb_dice_sums_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvtb_dice_grad_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvtb_wrap_fold_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "mvtb_wrap_odd_last_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "mvtb_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),

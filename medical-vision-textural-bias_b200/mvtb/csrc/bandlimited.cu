@@ -749,7 +749,7 @@ static void is_build_pattern(int A, int B, int lag, int spread, std::vector<unsi
 
 template <int NF>
 static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
-                  int F, float* minmax_out, int vols_per_sample, void* stream, SpFuse* sp) {
+                  int F, float* minmax_out, int vols_per_sample, void* stream, SpFuse* sp, const float* pre_abt) {
     BlGeom g;
     g.D = p->shape[0]; g.W = p->shape[1]; g.H = p->shape[2];
     g.F = F;
@@ -875,6 +875,10 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         const int nv = n_volumes - v0 < chunk ? n_volumes - v0 : chunk;
         cf* Y = p->bl_ws;
         cf* G = Y + (size_t)chunk * NF * g.NC;
+        // intensity prologue map: the cp.async forward kernel applies it as it reads; any other forward kernel gets the
+        // chunk mapped into its output slot first (the inverse pass overwrites that slot only after the forward pass)
+        const float* src = in + (size_t)v0 * p->vol_real;
+        const float* abt_v = pre_abt ? pre_abt + (size_t)3 * v0 : nullptr;
         bool tc_fwd = false;
 #ifndef MVTB_EMU
         const int tcN = (2 * NF + 15) / 16 * 16;
@@ -898,9 +902,15 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 // pruned DFT along H as a 3xTF32 GEMM on the tensor cores (bandlimited_tc.cuh)
                 TcFwdArgs ta;
                 CUtensorMap tmap;
-                int rcm = tc_make_tmap(&tmap, in + (size_t)v0 * p->vol_real, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, tc_bs * kTcRows);
+                if (abt_v) {
+                    int rca = mvtb_intensity_affine_f32(src, out + (size_t)v0 * p->vol_real, p->vol_real, nv, abt_v, stream);
+                    if (rca != MVTB_OK) return rca;
+                    src = out + (size_t)v0 * p->vol_real;
+                    abt_v = nullptr;
+                }
+                int rcm = tc_make_tmap(&tmap, src, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, tc_bs * kTcRows);
                 if (rcm != MVTB_OK) return rcm;
-                ta.x = in + (size_t)v0 * p->vol_real;
+                ta.x = src;
                 ta.Y = Y;
                 int rct = tc_fwd_table(p, NF, tcN, &ta.tab);
                 if (rct != MVTB_OK) return rct;
@@ -936,19 +946,28 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 else MVTB_LAUNCH(k_bl_fwd_tc<false>, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
             } else
 #endif
-            if (quad && NF <= 16 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && p->opt_async) {
+            {
+            const bool h4a = !tc_fwd && quad && NF <= 16 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && p->opt_async;
+            if (abt_v && !h4a) {
+                int rca = mvtb_intensity_affine_f32(src, out + (size_t)v0 * p->vol_real, p->vol_real, nv, abt_v, stream);
+                if (rca != MVTB_OK) return rca;
+                src = out + (size_t)v0 * p->vol_real;
+                abt_v = nullptr;
+            }
+            if (h4a) {
                 // cp.async staging ring: bytes in flight no longer limited by registers
                 const size_t smem_a = smem_h + sizeof(float) * kBlStages * 1024;
-                auto kern = k_bl_fwd_h4a<NF>;
-                MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_a, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1);
+                if (abt_v) { auto kern = k_bl_fwd_h4a<NF, true>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_a, stream, src, Y, g, ncb1, abt_v); }
+                else { auto kern = k_bl_fwd_h4a<NF, false>; MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_a, stream, src, Y, g, ncb1, abt_v); }
             } else if (quad) {
                 // one column per thread, 16 loads in flight, 3 CTAs/SM while the accumulators allow
                 auto kern = k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>;
-                MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, in + (size_t)v0 * p->vol_real, Y, g, ncb1);
+                MVTB_LAUNCH(kern, dim3((unsigned)(ncb1 * nv)), dim3(kColThreads), smem_h, stream, src, Y, g, ncb1);
             } else {
                 auto kern = k_bl_fwd_h<NF, CPT>;
                 MVTB_LAUNCH(kern, dim3((unsigned)(n_cblocks * nv)), dim3(kColThreads), smem_h, stream,
-                            in + (size_t)v0 * p->vol_real, Y, g, n_cblocks);
+                            src, Y, g, n_cblocks);
+            }
             }
         }
         const size_t bins = sizeof(cf) * (size_t)K * K;                      // shares the front of the buffer with the W table
@@ -1009,16 +1028,16 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
 }
 
 int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
-             int F, float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse) {
+             int F, float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse, const float* pre_abt) {
     SpFuse* sp = (SpFuse*)sp_fuse;
     switch (pick_nf(F + 1)) {
-        case 4: return bl_run<4>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 8: return bl_run<8>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 13: return bl_run<13>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 16: return bl_run<16>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 20: return bl_run<20>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 26: return bl_run<26>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
-        case 32: return bl_run<32>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp);
+        case 4: return bl_run<4>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 8: return bl_run<8>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 13: return bl_run<13>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 16: return bl_run<16>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 20: return bl_run<20>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 26: return bl_run<26>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
+        case 32: return bl_run<32>(p, in, out, n_volumes, desc, n_desc, F, minmax_out, vols_per_sample, stream, sp, pre_abt);
         default: set_error("band-limited path: F=%d not instantiated", F); return MVTB_EUNSUPPORTED;
     }
 }
@@ -1042,7 +1061,8 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_fwd_h4<NF, 1, 4, (NF > 16 ? 2 : 3)>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_h4<NF, CPT>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_h4v<NF>, optin)) != MVTB_OK) return rc;
-    if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF, false>, optin)) != MVTB_OK) return rc;
+    if (CPT == 2 && (rc = bl_big_smem(k_bl_fwd_h4a<NF, true>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 0>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 1>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 2>, optin)) != MVTB_OK) return rc;

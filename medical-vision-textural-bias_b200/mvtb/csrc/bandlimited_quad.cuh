@@ -512,9 +512,10 @@ static const int kBlStages = 8;
 
 // cp_async16 / cp_async_commit / cp_async_wait: mvtb_common.cuh
 
-template <int NF>
+// PRE: the intensity prologue map y = x != 0 ? a x + b : t of the volume (abt[3 vol ..]) is applied to every value read
+template <int NF, bool PRE>
 __global__ void __launch_bounds__(256, 3)
-k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks) {
+k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cblocks, const float* __restrict__ abt) {
     constexpr int NT = BlDims<NF>::NT, S = kBlStages;
     MVTB_DYN_SMEM(smem_raw);
     const int H = g.H, H2 = H / 2, H4 = H / 4;
@@ -524,6 +525,9 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
     const long long vol = blockIdx.x / n_cblocks;
     const long long c0 = (long long)(blockIdx.x - vol * n_cblocks) * 256;
     const float* xv = x + vol * H * g.NC;
+    float pa_ = 1.f, pb_ = 0.f, pt_ = 0.f;
+    if (PRE) { pa_ = __ldg(abt + 3 * vol); pb_ = __ldg(abt + 3 * vol + 1); pt_ = __ldg(abt + 3 * vol + 2); }
+#define MVTB_PRE(v) (PRE ? ((v) != 0.f ? fmaf(pa_, (v), pb_) : pt_) : (v))
 
     // this thread's 16-byte piece of every stage: row r of the quad, columns c0 + 4 j .. + 3
     const int r = tid >> 6, j = tid & 63;
@@ -554,10 +558,10 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
     {
         float2 cs[NF];
         bl_row<NF>(sc + H4 * NT, cs);
-        const float x0 = ld_stream(xv + colc);
-        const float xn = ld_stream(xv + (long long)H2 * g.NC + colc);
-        const float a = ld_stream(xv + (long long)H4 * g.NC + colc);
-        const float b = ld_stream(xv + (long long)(H - H4) * g.NC + colc);
+        const float x0 = MVTB_PRE(ld_stream(xv + colc));
+        const float xn = MVTB_PRE(ld_stream(xv + (long long)H2 * g.NC + colc));
+        const float a = MVTB_PRE(ld_stream(xv + (long long)H4 * g.NC + colc));
+        const float b = MVTB_PRE(ld_stream(xv + (long long)(H - H4) * g.NC + colc));
         const float2 eo = make_float2(a + b, b - a);
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) acc[f] = fma2(eo, cs[f], make_float2(x0 + ((f & 1) ? -xn : xn), 0.f));
@@ -574,7 +578,7 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
         }
         const float* st = ring + slot * 1024 + tid;
         slot = slot + 1 == S ? 0 : slot + 1;
-        const float a = st[0], b = st[256], c = st[512], d = st[768];
+        const float a = MVTB_PRE(st[0]), b = MVTB_PRE(st[256]), c = MVTB_PRE(st[512]), d = MVTB_PRE(st[768]);
         float2 cs[NF];
         bl_row<NF>(sc + q * NT, cs);
         const float s1 = a + b, s2 = c + d, d1 = a - b, d2 = c - d;
@@ -588,6 +592,7 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
         MVTB_UNROLL
         for (int f = 0; f < NF; ++f) yv[(long long)f * g.NC] = acc[f];
     }
+#undef MVTB_PRE
 }
 
 // ------------------------------------------------------------------ W axis, D axis and pointwise stage in one kernel

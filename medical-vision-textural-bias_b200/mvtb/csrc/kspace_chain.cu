@@ -28,7 +28,7 @@ namespace mvtb {
 // bandlimited.cu
 bool bl_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc, int* F_out);
 int bl_chain(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
-             int F, float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse);
+             int F, float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse, const float* pre_abt);
 
 // spike_fast.cu
 bool spike_fast_eligible(const mvtb_plan* p, const mvtb_chain_desc* desc, int n_desc);
@@ -700,9 +700,10 @@ static int launch_axis(mvtb_plan* p, cf* ws, int axis, int n_outer_vols, const C
 using namespace mvtb;
 
 // sp_fuse: null, or bandlimited.cu's SpFuse (the band-limited path may then run the select pass inside its inverse kernel)
+// pre_abt: null, or the intensity prologue map per volume (applied on load by the band-limited path, else by its own pass)
 static int chain_impl(mvtb_plan* p, const float* in, float* out, int n_volumes,
                       const mvtb_chain_desc* desc, int n_desc,
-                      float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse) {
+                      float* minmax_out, int vols_per_sample, void* stream, void* sp_fuse, const float* pre_abt) {
     if (!p || !in || !out || !desc) { set_error("chain: null argument"); return MVTB_EINVAL; }
     if (n_volumes < 0) { set_error("chain: n_volumes=%d", n_volumes); return MVTB_EINVAL; }
     if (n_desc != 1 && n_desc != n_volumes) { set_error("chain: n_desc=%d must be 1 or n_volumes=%d", n_desc, n_volumes); return MVTB_EINVAL; }
@@ -746,11 +747,18 @@ static int chain_impl(mvtb_plan* p, const float* in, float* out, int n_volumes,
         MVTB_LAUNCH(k_minmax_init, dim3((n_samples + 127) / 128), dim3(128), 0, stream, minmax_out, n_samples);
     }
 
-    if (spike_fast_eligible(p, desc, n_desc))
-        return spike_fast_chain(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream);
     int blF = 0;
-    if (bl_eligible(p, desc, n_desc, &blF))
-        return bl_chain(p, in, out, n_volumes, desc, n_desc, blF, minmax_out, vols_per_sample, stream, sp_fuse);
+    const bool spike_fast = spike_fast_eligible(p, desc, n_desc);
+    const bool bl = !spike_fast && bl_eligible(p, desc, n_desc, &blF);
+    if (pre_abt && !bl) {                              // the other paths read a prepared volume: map it into `out` first
+        int rc = mvtb_intensity_affine_f32(in, out, p->vol_real, n_volumes, pre_abt, stream);
+        if (rc != MVTB_OK) return rc;
+        in = out;
+    }
+    if (spike_fast)
+        return spike_fast_chain(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream);
+    if (bl)
+        return bl_chain(p, in, out, n_volumes, desc, n_desc, blF, minmax_out, vols_per_sample, stream, sp_fuse, pre_abt);
 
     const DescDev* ddesc = nullptr;                    // device copy of the converted descriptors, valid on `stream`
     {
@@ -805,12 +813,14 @@ static int chain_impl(mvtb_plan* p, const float* in, float* out, int n_volumes,
 extern "C" int mvtb_kspace_chain_f32(mvtb_plan* p, const float* in, float* out, int n_volumes,
                                      const mvtb_chain_desc* desc, int n_desc,
                                      float* minmax_out, int vols_per_sample, void* stream) {
-    return chain_impl(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream, nullptr);
+    return chain_impl(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream, nullptr, nullptr);
 }
 
-extern "C" int mvtb_kspace_chain_sp_f32(mvtb_plan* p, const float* in, float* out, int n_volumes,
-                                        const mvtb_chain_desc* desc, int n_desc, float* minmax_out, int vols_per_sample,
-                                        float prob, uint64_t seed, uint64_t offset, void* stream) {
+extern "C" int mvtb_kspace_chain_ex_f32(mvtb_plan* p, const float* in, float* out, int n_volumes,
+                                        const mvtb_chain_desc* desc, int n_desc, const float* pre_abt, float* minmax_out,
+                                        int vols_per_sample, const mvtb_sp_params* spp, void* stream) {
+    if (!spp) return chain_impl(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream, nullptr, pre_abt);
+    const float prob = spp->p;
     if (!p || !minmax_out) { set_error("chain_sp: null plan or minmax_out"); return MVTB_EINVAL; }
     if (!(prob >= 0.f && prob <= 1.f)) { set_error("chain_sp: p=%g outside [0,1] (the caller clamps, F:444)", (double)prob); return MVTB_EINVAL; }
     if (vols_per_sample < 1 || n_volumes < 0 || n_volumes % vols_per_sample != 0) {
@@ -819,8 +829,8 @@ extern "C" int mvtb_kspace_chain_sp_f32(mvtb_plan* p, const float* in, float* ou
     }
     if (n_volumes / vols_per_sample > 65535) { set_error("chain_sp: more than 65535 samples in one call"); return MVTB_EUNSUPPORTED; }
     SpFuse sp;
-    sp.p = prob; sp.seed = seed; sp.offset = offset; sp.done = false;
-    int rc = chain_impl(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream, &sp);
+    sp.p = prob; sp.seed = spp->seed; sp.offset = spp->offset; sp.done = false;
+    int rc = chain_impl(p, in, out, n_volumes, desc, n_desc, minmax_out, vols_per_sample, stream, &sp, pre_abt);
     if (rc != MVTB_OK || sp.done || prob == 0.f || n_volumes == 0) return rc;
     // any other path: the select pass follows as its own kernel (same Philox counters, same result)
     unsigned host_table[MVTB_SP_BLOCK];
@@ -829,8 +839,16 @@ extern "C" int mvtb_kspace_chain_sp_f32(mvtb_plan* p, const float* in, float* ou
     void* dtab = nullptr;
     rc = plan_stage_upload(p, host_table, sizeof(host_table), stream, &dtab);
     if (rc != MVTB_OK) return rc;
-    return sparse_sp_launch(out, (size_t)vols_per_sample * p->vol_real, n_volumes / vols_per_sample, seed, offset, prob,
+    return sparse_sp_launch(out, (size_t)vols_per_sample * p->vol_real, n_volumes / vols_per_sample, spp->seed, spp->offset, prob,
                             minmax_out, (const unsigned*)dtab, stream);
+}
+
+extern "C" int mvtb_kspace_chain_sp_f32(mvtb_plan* p, const float* in, float* out, int n_volumes,
+                                        const mvtb_chain_desc* desc, int n_desc, float* minmax_out, int vols_per_sample,
+                                        float prob, uint64_t seed, uint64_t offset, void* stream) {
+    mvtb_sp_params sp;
+    sp.p = prob; sp.seed = seed; sp.offset = offset;
+    return mvtb_kspace_chain_ex_f32(p, in, out, n_volumes, desc, n_desc, nullptr, minmax_out, vols_per_sample, &sp, stream);
 }
 
 extern "C" int mvtb_kspace_logabs_sum_f32(mvtb_plan* p, const float* in, int n_volumes, double* sums_out, void* stream) {

@@ -197,6 +197,101 @@ def kspace_chain_sp(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDe
     return y, mm
 
 
+def kspace_chain_ex(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc], *, pre_abt: Optional[torch.Tensor] = None,
+                    sp: Optional[Tuple[float, int, int]] = None, want_minmax: bool = False, vols_per_sample: int = 1,
+                    out: Optional[torch.Tensor] = None):
+    """mvtb_kspace_chain_ex_f32: [intensity prologue map on the way in] -> chain -> [sparse salt-and-pepper on the way
+    out].  pre_abt: float32 CUDA tensor (n_volumes, 3) from intensity_coeffs(); sp: (p, seed, offset).
+    Returns y, or (y, minmax) when want_minmax or sp is given."""
+    L = _lib.lib()
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("kspace_chain_ex expects a contiguous float32 CUDA tensor (use functional.to_device)")
+    fft_shape = tuple(x.shape[-ndim_fft:])
+    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    if len(descs) not in (1, nvol):
+        raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
+    if pre_abt is not None and (pre_abt.shape != (nvol, 3) or pre_abt.dtype != torch.float32 or pre_abt.device != x.device or not pre_abt.is_contiguous()):
+        raise ValueError("pre_abt must be a contiguous float32 (n_volumes, 3) tensor on x's device")
+    y = torch.empty_like(x) if out is None else out
+    need_mm = want_minmax or sp is not None
+    mm = torch.empty(((nvol + vols_per_sample - 1) // vols_per_sample, 2), dtype=torch.float32, device=x.device) if need_mm else None
+    if x.numel() == 0:
+        return (y, mm) if need_mm else y
+    plan = get_plan(fft_shape, nvol, x.device)
+    spp = None
+    if sp is not None:
+        spp = _lib.SpParams(float(sp[0]), int(sp[1]) & (2 ** 64 - 1), int(sp[2]) & (2 ** 64 - 1))
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_kspace_chain_ex_f32(plan, _ptr(x), _ptr(y), nvol, host.desc_array(descs), len(descs), _ptr(pre_abt), _ptr(mm),
+                                        int(vols_per_sample), C.byref(spp) if spp is not None else None, _stream(x.device))
+    _lib.check(L, rc)
+    return (y, mm) if need_mm else y
+
+
+# ----------------------------------------------------------------------------- intensity prologue (csrc/intensity.cu)
+def intensity_coeffs(x: torch.Tensor, n_channels: int, *, scale=None, shift=None, want_stats: bool = False):
+    """One read of x (n_channels contiguous channels): per channel the map (a, b, t) of
+    NormalizeIntensity(nonzero, channel_wise) -> * scale -> + shift, i.e. y = x != 0 ? a x + b : t.
+    scale / shift: None, a number, or one value per channel.  Returns abt (n_channels, 3) float32 on x.device
+    [, stats (n_channels, 3) float64: count, mean, std]."""
+    L = _lib.lib()
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("intensity_coeffs expects a contiguous float32 CUDA tensor")
+    dev = x.device
+
+    def vec(v, default):
+        if v is None:
+            return None
+        t = torch.as_tensor(v, dtype=torch.float32).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(n_channels)
+        if t.numel() != n_channels:
+            raise ValueError(f"need 1 or {n_channels} values")
+        return t.contiguous().to(dev, non_blocking=True)
+
+    sc, sh = vec(scale, 1.0), vec(shift, 0.0)
+    abt = torch.empty((n_channels, 3), dtype=torch.float32, device=dev)
+    stats = torch.empty((n_channels, 3), dtype=torch.float64, device=dev) if want_stats else None
+    scratch = torch.empty(max(int(L.mvtb_intensity_scratch_bytes(n_channels)), 8), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.mvtb_intensity_prologue_coeffs_f32(_ptr(x), x.numel() // max(n_channels, 1), n_channels, _ptr(sc), _ptr(sh),
+                                                  _ptr(stats), _ptr(abt), _ptr(scratch), _stream(dev))
+    _lib.check(L, rc)
+    return (abt, stats) if want_stats else abt
+
+
+def intensity_affine(x: torch.Tensor, abt: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x != 0 ? a x + b : t with one (a, b, t) per leading block of x (abt: (n, 3))."""
+    L = _lib.lib()
+    n = int(abt.shape[0])
+    y = torch.empty_like(x) if out is None else out
+    if x.numel() == 0:
+        return y
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_intensity_affine_f32(_ptr(x), _ptr(y), x.numel() // n, n, _ptr(abt), _stream(x.device))
+    _lib.check(L, rc)
+    return y
+
+
+def intensity_prologue(img, *, nonzero: bool = True, channel_wise: bool = True, scale: float = 1.0, shift: float = 0.0):
+    """NormalizeIntensity(nonzero, channel_wise) -> * scale -> + shift on a (C, ...) image (tensor or numpy array, any
+    device); the result comes back where the input lived, float32."""
+    if not nonzero:
+        raise NotImplementedError("only nonzero=True (the reference's setting) is built")
+    x, org = to_device(img)
+    n_ch = int(x.shape[0]) if channel_wise else 1
+    abt = intensity_coeffs(x, n_ch, scale=scale, shift=shift)
+    y = back(intensity_affine(x, abt), Origin(org.device, torch.float32))
+    return y.numpy() if isinstance(img, np.ndarray) else y
+
+
+def intensity_scale_shift(img, *, scale: float = 1.0, shift: float = 0.0):
+    """ScaleIntensity(factor) / ShiftIntensity(offset) on their own: y = x * scale + shift for every voxel."""
+    x, org = to_device(img)
+    y = back(torch.addcmul(torch.full((), float(shift), device=x.device), x, torch.full((), float(scale), device=x.device)), Origin(org.device, torch.float32))
+    return y.numpy() if isinstance(img, np.ndarray) else y
+
+
 def logabs_mean25(x: torch.Tensor, ndim_fft: int) -> torch.Tensor:
     """2.5 * mean(log(|fftn(x)| + 1e-10)) per volume, float32 on x.device (F:932-933, F:1127-1129)."""
     L = _lib.lib()

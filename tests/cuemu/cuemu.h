@@ -129,6 +129,7 @@ static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline void sincospif(float x, float* s, float* c) { *s = (float)std::sin(M_PI * (double)x); *c = (float)std::cos(M_PI * (double)x); }
+static inline float expf_(float x) { return std::exp(x); }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __int2float_rn(int i) { return (float)i; }
 static inline float __uint2float_rn(unsigned i) { return (float)i; }
