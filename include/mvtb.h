@@ -45,6 +45,11 @@ extern "C" {
  * GibbsNoiseLayer S:99-109; i_d = fftshift-ed index; threshold found on the host by evaluating
  * the reference's own fp64 / fp32 predicate, which is monotone in the sum) */
 #define MVTB_MASK_CENTRED 2
+/* keep  <=>  mask_u[fftshift-ed index] > mask_p, mask_u a device array of the volume's full k-space shape: RandZF's
+ * random zero-filling (50_reconstruction/reconGan/utils2.py:34-74: `mask = torch.rand(k.size()); k[mask <= p] = 0`).
+ * The mask is not Hermitian; as for every mask the real part taken afterwards makes it (M(f) + M(-f)) / 2.  General
+ * FFT path only; mask_ndim is ignored (the array covers all FFT axes). */
+#define MVTB_MASK_UNIFORM 3
 
 typedef struct mvtb_spike {
     int32_t idx[MVTB_MAX_FFT_DIMS]; /* fftshift-ed k-space index per FFT axis, outermost first
@@ -66,6 +71,9 @@ typedef struct mvtb_chain_desc {
     float wrap_alpha;      /* weight of odd fftshift-ed indices (F:509-511) */
     int32_t wrap_naxes;    /* 0 = no wrap; else the trailing wrap_naxes axes are weighted (3 in the reference) */
     mvtb_spike spikes[MVTB_MAX_SPIKES];
+    const float* mask_u;   /* MVTB_MASK_UNIFORM: device pointer to this volume's uniform field (else NULL) */
+    float mask_p;          /* MVTB_MASK_UNIFORM: threshold */
+    int32_t reserved;
 } mvtb_chain_desc;
 
 typedef struct mvtb_plan mvtb_plan;
@@ -173,6 +181,11 @@ int mvtb_dice_sums_f32(const float* x, const float* target, size_t n_per_vol, in
                        double* sums_out, void* scratch, void* stream);
 int mvtb_dice_grad_f32(const float* x, const float* target, size_t n_per_vol, int n_vols, int from_logits,
                        const float* coef, float* grad_out, void* stream);
+
+/* sum_i (a_i - b_i)^2 -> device double (deterministic).  scratch: mvtb_dice_scratch_bytes(1) bytes.  With fftn
+ * unnormalised over (H, W), MSE(Re fftn a, Re fftn b) + MSE(Im fftn a, Im fftn b) = H W MSE(a, b) (Parseval): the
+ * frequency-consistency loss of 50_reconstruction/reconGan/reconGan_freq.py:134-140 needs no transform. */
+int mvtb_sqdiff_sum_f32(const float* a, const float* b, size_t n, double* sum_out, void* scratch, void* stream);
 
 /* WrapArtifact (F:503-515) on (C,H,W,D) when H, W and D are all even: the image-domain fold
  * out = prod_axes (c0 + s c1 Roll_{N/2}) x, c0=(1+alpha)/2, c1=(1-alpha)/2, s=(-1)^(N/2)

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvtb.so")
 
 MVTB_OK, MVTB_EINVAL, MVTB_EUNSUPPORTED, MVTB_ENOMEM, MVTB_ENODEVICE = 0, -1, -2, -3, -4
-MASK_NONE, MASK_DISK, MASK_CENTRED = 0, 1, 2
+MASK_NONE, MASK_DISK, MASK_CENTRED, MASK_UNIFORM = 0, 1, 2, 3
 MAX_FFT_DIMS, MAX_SPIKES = 4, 8
 
 
@@ -29,6 +29,9 @@ class ChainDesc(C.Structure):
         ("wrap_alpha", C.c_float),
         ("wrap_naxes", C.c_int32),
         ("spikes", Spike * MAX_SPIKES),
+        ("mask_u", C.c_void_p),
+        ("mask_p", C.c_float),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -69,6 +72,7 @@ _SYMBOLS = {
     "mvtb_dice_scratch_bytes": (C.c_size_t, [C.c_int]),
     "mvtb_dice_sums_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvtb_dice_grad_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mvtb_sqdiff_sum_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mvtb_wrap_fold_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "mvtb_wrap_odd_last_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "mvtb_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),

@@ -83,6 +83,36 @@ k_dice_grad(const float* __restrict__ x, const float* __restrict__ t, size_t n_p
     }
 }
 
+// sum (a - b)^2 in double, one partial per CTA (fixed order): the frequency-consistency loss of the reconstruction GAN
+// (50_reconstruction/reconGan/reconGan_freq.py:134-140) is, by Parseval, H W times the image-domain mean squared error
+__global__ void __launch_bounds__(kDiceThreads)
+k_sqdiff(const float* __restrict__ a, const float* __restrict__ b, size_t n, double* __restrict__ partial) {
+    double s = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) {
+        const float d = a[e] - b[e];
+        s += (double)d * (double)d;
+    }
+    __shared__ double red[kDiceThreads / 32];
+    MVTB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < kDiceThreads / 32; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(32)
+k_sum_partials(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) s += partial[i];
+    MVTB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
 }  // namespace mvtb
 
 using namespace mvtb;
@@ -119,6 +149,18 @@ extern "C" int mvtb_dice_grad_f32(const float* x, const float* target, size_t n_
     if (n_vols == 0 || n_per_vol == 0) return MVTB_OK;
     const unsigned bx = dice_bx(n_per_vol, n_vols);
     MVTB_LAUNCH(k_dice_grad, dim3(bx, (unsigned)n_vols), dim3(256), 0, stream, x, target, n_per_vol, from_logits, coef, grad_out);
+    MVTB_CUDA(cudaGetLastError());
+    return MVTB_OK;
+}
+
+extern "C" int mvtb_sqdiff_sum_f32(const float* a, const float* b, size_t n, double* sum_out, void* scratch, void* stream) {
+    if (!a || !b || !sum_out || !scratch) { set_error("sqdiff_sum: null argument"); return MVTB_EINVAL; }
+    if (n == 0) { MVTB_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), (cudaStream_t)stream)); return MVTB_OK; }
+    size_t want = (n / 4 + kDiceThreads - 1) / kDiceThreads;
+    if (want < 1) want = 1;
+    const unsigned bx = (unsigned)(want < (size_t)kDiceBlocksCap ? want : (size_t)kDiceBlocksCap);
+    MVTB_LAUNCH(k_sqdiff, dim3(bx), dim3(kDiceThreads), 0, stream, a, b, n, (double*)scratch);
+    MVTB_LAUNCH(k_sum_partials, dim3(1), dim3(32), 0, stream, (const double*)scratch, (int)bx, sum_out);
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;
 }

@@ -340,6 +340,7 @@ k_wrap_fold_hw(const float* __restrict__ in, float* __restrict__ out, int H, int
 
 // ------------------------------------------------------------------ pointwise k-space stage
 __device__ __forceinline__ long long mask_term(int kind, int i, int n) {
+    if (kind == MVTB_MASK_UNIFORM) return 0;
     const long long d = kind == MVTB_MASK_DISK ? (long long)(i - n / 2) : (long long)(2 * i - (n - 1));
     return d * d;
 }
@@ -373,6 +374,8 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
     // spike on it) is zero whatever the data, so it is neither loaded nor transformed -- 40 % of the tiles for
     // GibbsNoise(0.5) on 240 x 240 x 155, 85 % for a disk of radius 40.
     long long qp = 0, qn = 0;
+    long long up_off = 0, un_off = 0;      // MVTB_MASK_UNIFORM: offset of the column (and of its mirror) in the uniform field
+    long long u_stride = 1;                // ... and the stride of this axis there
     float wgt = g.scale;
     unsigned mpos = 0, mneg = 0;           // per-spike "all lower axes match" bits
     if (MODE == AX_MID) {
@@ -397,6 +400,9 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
                 qn += mask_term(d.mask_kind, ineg[b], nb);
             }
             if (b < d.wrap_naxes && (ish[b] & 1)) wgt *= d.wrap_alpha;
+            up_off += (long long)ish[b] * u_stride;
+            un_off += (long long)ineg[b] * u_stride;
+            u_stride *= nb;
         }
         for (int sI = 0; sI < d.n_spikes; ++sI) {
             bool pm = true, qm = true;
@@ -408,7 +414,7 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             mneg |= (qm ? 1u : 0u) << sI;
         }
         bool col_dead = !col_ok;
-        if (col_ok && d.mask_kind != MVTB_MASK_NONE && !d.inside_off && (mpos | mneg) == 0u) {
+        if (col_ok && d.mask_kind != MVTB_MASK_NONE && d.mask_kind != MVTB_MASK_UNIFORM && !d.inside_off && (mpos | mneg) == 0u) {
             // smallest term this axis can add: 0, or 1 for a centred mask on an even axis ((2i - (n-1))^2 is odd)
             const long long tmin = (axis < d.mask_ndim && d.mask_kind != MVTB_MASK_DISK && !(n & 1)) ? 1 : 0;
             col_dead = qp + tmin > d.thr && qn + tmin > d.thr;
@@ -471,7 +477,12 @@ k_axis(cf* __restrict__ ws, AxisDev ax, int axis, long long inner, int T, int nt
             for (int j = tid >> lgT; j < n; j += nthr >> lgT) {
                 const int4 e = tab[j];
                 float meff = 1.f;
-                if (any_mask) {
+                if (d.mask_kind == MVTB_MASK_UNIFORM) {              // RandZF: keep <=> u > p at the bin, at its mirror
+                    const int imn_ = (2 * (n / 2) - e.x + n) % n;
+                    const int kp = (__ldg(d.mask_u + up_off + (long long)e.x * u_stride) > d.mask_p ? 1 : 0) ^ d.inside_off;
+                    const int kn = (__ldg(d.mask_u + un_off + (long long)imn_ * u_stride) > d.mask_p ? 1 : 0) ^ d.inside_off;
+                    meff = 0.5f * (float)(kp + kn);
+                } else if (any_mask) {
                     const int kp = (qp + e.y <= d.thr ? 1 : 0) ^ d.inside_off;
                     const int kn = (qn + e.z <= d.thr ? 1 : 0) ^ d.inside_off;
                     meff = 0.5f * (float)(kp + kn);
@@ -607,6 +618,7 @@ static ChainGeom make_geom(const mvtb_plan* p) {
 }
 
 static bool same_desc(const mvtb_chain_desc& a, const mvtb_chain_desc& b) {
+    if (a.mask_kind == MVTB_MASK_UNIFORM || b.mask_kind == MVTB_MASK_UNIFORM) return false;    // every volume has its own field
     if (a.mask_kind != b.mask_kind || a.mask_ndim != b.mask_ndim || a.mask_thresh != b.mask_thresh || a.inside_off != b.inside_off ||
         a.n_spikes != b.n_spikes || a.wrap_naxes != b.wrap_naxes || memcmp(&a.wrap_alpha, &b.wrap_alpha, sizeof(float)) != 0) return false;
     if (a.n_spikes < 0 || a.n_spikes > MVTB_MAX_SPIKES) return false;
@@ -619,12 +631,17 @@ static bool same_desc(const mvtb_chain_desc& a, const mvtb_chain_desc& b) {
 // validates one user descriptor against the plan and converts it to the device view
 int convert_desc(const mvtb_plan* p, const mvtb_chain_desc* u, DescDev* d) {
     memset(d, 0, sizeof(*d));
-    if (u->mask_kind < MVTB_MASK_NONE || u->mask_kind > MVTB_MASK_CENTRED) { set_error("chain: mask_kind=%d", u->mask_kind); return MVTB_EINVAL; }
-    if (u->mask_kind != MVTB_MASK_NONE && (u->mask_ndim < 1 || u->mask_ndim > p->ndim)) { set_error("chain: mask_ndim=%d with ndim_fft=%d", u->mask_ndim, p->ndim); return MVTB_EINVAL; }
+    if (u->mask_kind < MVTB_MASK_NONE || u->mask_kind > MVTB_MASK_UNIFORM) { set_error("chain: mask_kind=%d", u->mask_kind); return MVTB_EINVAL; }
+    if (u->mask_kind == MVTB_MASK_UNIFORM && !u->mask_u) { set_error("chain: MVTB_MASK_UNIFORM needs mask_u"); return MVTB_EINVAL; }
+    if (u->mask_kind == MVTB_MASK_UNIFORM && u->n_spikes > 0) { set_error("chain: spikes cannot be combined with MVTB_MASK_UNIFORM"); return MVTB_EUNSUPPORTED; }
+    if (u->mask_kind == MVTB_MASK_UNIFORM && p->lead_drop > 0) { set_error("chain: MVTB_MASK_UNIFORM with leading axes of length 1 is not built"); return MVTB_EUNSUPPORTED; }
+    if (u->mask_kind != MVTB_MASK_NONE && u->mask_kind != MVTB_MASK_UNIFORM && (u->mask_ndim < 1 || u->mask_ndim > p->ndim)) { set_error("chain: mask_ndim=%d with ndim_fft=%d", u->mask_ndim, p->ndim); return MVTB_EINVAL; }
     if (u->n_spikes < 0 || u->n_spikes > MVTB_MAX_SPIKES) { set_error("chain: n_spikes=%d (max %d)", u->n_spikes, MVTB_MAX_SPIKES); return MVTB_EUNSUPPORTED; }
     if (u->wrap_naxes < 0 || u->wrap_naxes > p->ndim) { set_error("chain: wrap_naxes=%d", u->wrap_naxes); return MVTB_EINVAL; }
     d->mask_kind = u->mask_kind;
-    d->mask_ndim = u->mask_kind == MVTB_MASK_NONE ? 0 : u->mask_ndim;
+    d->mask_ndim = u->mask_kind == MVTB_MASK_NONE ? 0 : (u->mask_kind == MVTB_MASK_UNIFORM ? p->ndim : u->mask_ndim);
+    d->mask_u = u->mask_kind == MVTB_MASK_UNIFORM ? u->mask_u : nullptr;
+    d->mask_p = u->mask_p;
     d->thr = u->mask_thresh;
     d->inside_off = u->inside_off ? 1 : 0;
     d->n_spikes = u->n_spikes;

@@ -137,6 +137,9 @@ struct DescDev {
     float wrap_alpha;
     int wrap_naxes;
     SpikeDev sp[MVTB_MAX_SPIKES];
+    const float* mask_u;         // MVTB_MASK_UNIFORM: the volume's uniform field, full fftshift-ed layout
+    float mask_p;
+    int pad_;
 };
 
 }  // namespace mvtb

@@ -95,7 +95,7 @@ def exp_f32(log_intensity: float) -> float:
 
 def make_desc(*, mask_kind: int = _lib.MASK_NONE, mask_ndim: int = 0, mask_thresh: int = 0, inside_off: bool = False,
               spikes: Iterable[Tuple[Sequence[int], float]] = (), wrap_alpha: Optional[float] = None,
-              wrap_naxes: int = 3) -> _lib.ChainDesc:
+              wrap_naxes: int = 3, mask_u: int = 0, mask_p: float = 0.0) -> _lib.ChainDesc:
     """Build one mvtb_chain_desc.  spikes: (fftshift-ed index per FFT axis outermost first, amplitude);
     later entries at the same location replace earlier ones (the reference overwrites, F:937-938)."""
     d = _lib.ChainDesc()
@@ -113,6 +113,8 @@ def make_desc(*, mask_kind: int = _lib.MASK_NONE, mask_ndim: int = 0, mask_thres
         for j, i in enumerate(idx):
             d.spikes[s].idx[j] = i
         d.spikes[s].amplitude = amp
+    d.mask_u = int(mask_u) or None           # MASK_UNIFORM: device address of the volume's uniform field (the caller keeps it alive)
+    d.mask_p = float(mask_p)
     if wrap_alpha is None:
         d.wrap_alpha, d.wrap_naxes = 1.0, 0
     else:

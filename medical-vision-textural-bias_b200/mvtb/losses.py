@@ -130,3 +130,36 @@ def dice_loss_and_metric(logits: torch.Tensor, target: torch.Tensor, smooth_nr: 
     s = dice_sums(logits, target, from_logits=True)
     f = 1.0 - (2.0 * s[..., 0] + smooth_nr) / (s[..., 1] + s[..., 2] + smooth_dr)
     return f.mean().to(torch.float32), _metric_from_sums(s)
+
+
+class _FreqConsistencyFn(torch.autograd.Function):
+    """MSE(Re fftn real, Re fftn fake) + MSE(Im fftn real, Im fftn fake) over the last two axes (reconGan_freq.py:134-140)
+    = H W * MSE(real, fake) by Parseval (the transform is unnormalised): one fused squared-difference reduction."""
+
+    @staticmethod
+    def forward(ctx, real, fake):
+        require_cuda()
+        if real.shape != fake.shape or real.dim() < 2:
+            raise ValueError("freq_consistency_loss: shapes differ")
+        a = real.detach().to(torch.float32).contiguous()
+        b = fake.detach().to(torch.float32).contiguous()
+        L = _lib.lib()
+        out = torch.empty(1, dtype=torch.float64, device=a.device)
+        scratch = torch.empty(max(int(L.mvtb_dice_scratch_bytes(1)), 8), dtype=torch.uint8, device=a.device)
+        with torch.cuda.device(a.device):
+            rc = L.mvtb_sqdiff_sum_f32(_ptr(a), _ptr(b), a.numel(), _ptr(out), _ptr(scratch), _stream(a.device))
+        _lib.check(L, rc)
+        hw = float(a.shape[-1] * a.shape[-2])
+        ctx.save_for_backward(a, b)
+        ctx.c = 2.0 * hw / max(a.numel(), 1)
+        return (out[0] * (hw / max(a.numel(), 1))).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        d = (a - b) * (g * ctx.c)
+        return d, -d
+
+
+def freq_consistency_loss(real: torch.Tensor, fake: torch.Tensor) -> torch.Tensor:
+    return _FreqConsistencyFn.apply(real, fake)
