@@ -125,7 +125,7 @@ def test_cabi_exports_every_declared_symbol():
         build.build_library()
     lib = B.bind(C.CDLL(B.LIB_PATH))          # raises AttributeError on a missing export
     assert lib.mvtb_version() == 200
-    assert C.sizeof(B.ChainDesc) == 32 + 8 * 24 and C.sizeof(B.Spike) == 24
+    assert C.sizeof(B.ChainDesc) == 32 + 8 * 24 + 16 and C.sizeof(B.Spike) == 24       # + mask_u, mask_p, reserved
 
 
 def test_no_cpu_fallback_without_cuda():
