@@ -50,7 +50,12 @@ WORKLOADS = {
     "cfg3": dict(name="Gibbs disk r=12.5 + salt-and-pepper 0.15 on 4-channel samples",
                  channels=4, batch=16, r=12.5, spike=False, alpha=None, p=0.15),
     "cfg1": dict(name="Gibbs disk r=12.5 (RandFourierDiskMaskd)", channels=1, batch=64, r=12.5, spike=False, alpha=None, p=None),
+    # BASELINE.json configs[2] as written: 256 samples in total, sharded 256/128/64/32 per GPU at 1/2/4/8 GPUs (strong scaling)
+    "cfg3s": dict(name="Gibbs disk r=12.5 + salt-and-pepper 0.15 on 4-channel samples, 256 samples in total (strong scaling)",
+                  channels=4, batch=256, strong_total=256, r=12.5, spike=False, alpha=None, p=0.15),
 }
+# configs[3] and configs[4] of BASELINE.json have other units of work (2-D slices; 128x128x64 crops): bench.py --workload cfg4|cfg5
+AUX_WORKLOADS = ("cfg4", "cfg5")
 
 
 def peak_hbm():
@@ -139,54 +144,91 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_step(cfg, sample_index, n_volumes):
-    """The reference's CPU path (oracle port, same torch op sequence) on n_volumes samples."""
+def reference_modules():
+    """The UNMODIFIED reference (oracle/_ref, placed by oracle/build_ref.py, imported through oracle/monai_shim), or None."""
+    try:
+        from oracle import build_ref
+        return build_ref.import_reference()
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def cpu_reference_step(cfg, sample_index, n_volumes, mods=None):
+    """The reference's CPU path on n_volumes samples; yields the transform time of each.  With `mods` the reference's
+    own classes run (kind "reference"); without, oracle/ref_port.py (kind "port": the same torch op sequence)."""
     from oracle import ref_port as P
     C = cfg["channels"]
     idxs = spike_indices(sample_index, n_volumes) if cfg["spike"] else [None] * n_volumes
+    chain = None
+    if mods is not None:
+        RF = mods[0]
+        chain = [RF.RandFourierDiskMaskd(keys='image', r=cfg["r"], inside_off=False, prob=1.)]
+        if cfg["spike"]:
+            chain.append(RF.RandPlaneWaves_ellipsoid('image', 55., 55., 30., intensity_value=15., prob=1.))
+        if cfg["alpha"] is not None:
+            chain.append(RF.WrapArtifactd("image", cfg["alpha"]))
+        if cfg["p"] is not None:
+            chain.append(RF.SaltAndPepper(cfg["p"]))
     for i in range(n_volumes):
         x = P.synthetic_volume(sample_index + i, (C,) + SHAPE)
         t0 = time.perf_counter()
-        y = P.fourier_disk_mask(x, cfg["r"], False)
-        if cfg["spike"]:
-            y = P.plane_wave_spike(y, idxs[i], 15.0)
-        if cfg["alpha"] is not None:
-            y = P.wrap_artifact(y, cfg["alpha"])
-        if cfg["p"] is not None:
-            y = P.salt_and_pepper(y, cfg["p"], torch.rand(y.size()))      # the reference draws u itself (F:472)
+        if chain is not None:
+            d = {"image": x}
+            for tr in chain:
+                d = tr(d)
+        else:
+            y = P.fourier_disk_mask(x, cfg["r"], False)
+            if cfg["spike"]:
+                y = P.plane_wave_spike(y, idxs[i], 15.0)
+            if cfg["alpha"] is not None:
+                y = P.wrap_artifact(y, cfg["alpha"])
+            if cfg["p"] is not None:
+                y = P.salt_and_pepper(y, cfg["p"], torch.rand(y.size()))      # the reference draws u itself (F:472)
         yield time.perf_counter() - t0
 
 
 def time_cpu_reference(cfg, n_volumes, warm=1):
+    """(volumes/s on all host threads, threads, per-volume times, volumes/s on ONE thread, kind)."""
+    mods = reference_modules()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    list(cpu_reference_step(cfg, 10_000, warm))
-    ts = list(cpu_reference_step(cfg, 0, n_volumes))
-    return n_volumes / sum(ts), cores, ts
+    list(cpu_reference_step(cfg, 10_000, warm, mods))
+    ts = list(cpu_reference_step(cfg, 0, n_volumes, mods))
+    torch.set_num_threads(1)
+    t1 = list(cpu_reference_step(cfg, 0, 1, mods))
+    torch.set_num_threads(cores)
+    return n_volumes / sum(ts), cores, ts, 1.0 / sum(t1), ("reference" if mods is not None else "port")
 
 
 def run_reference_arm(args, cfg, rank):
     if rank != 0:
         return
+    mods = reference_modules()
+    kind = "reference" if mods is not None else "port"
     n_per_step = 1 if cfg["channels"] > 1 else 2
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    list(cpu_reference_step(cfg, 10_000, 1))
+    list(cpu_reference_step(cfg, 10_000, 1, mods))
     for _ in range(args.warmup):
-        list(cpu_reference_step(cfg, 20_000, n_per_step))
+        list(cpu_reference_step(cfg, 20_000, n_per_step, mods))
     dt = 0.0                               # transform time only; generating the synthetic input is not timed
     for s in range(args.steps):
-        dt += sum(cpu_reference_step(cfg, s * n_per_step, n_per_step))
+        dt += sum(cpu_reference_step(cfg, s * n_per_step, n_per_step, mods))
     value = args.steps * n_per_step / dt
+    torch.set_num_threads(1)
+    one = 1.0 / sum(cpu_reference_step(cfg, 0, 1, mods))
+    torch.set_num_threads(cores)
     sample = f"{n_per_step} sample(s) of {cfg['channels']}x240x240x155 per step, {args.steps} steps, torch {torch.__version__} CPU, {cores} threads"
+    what = ("the UNMODIFIED reference classes (oracle/_ref = source_code/filters_and_operators.py, through oracle/monai_shim)" if mods is not None else
+            "oracle/ref_port.py, the bit-identical restatement of filters_and_operators.py (oracle/_ref is absent on this box)")
     line = {
         "impl": "reference", "metric": "volumes/sec (240x240x155 fp32)", "value": value, "unit": "volumes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % cfg["channels"],
-                   "volumes_per_step": n_per_step, "note": "reference CPU path = oracle/ref_port.py, the bit-identical restatement "
-                   "of filters_and_operators.py (the pure-Python reference cannot travel to the GPU box)"},
-        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": cores, "kind": "port", "sample": sample},
+                   "volumes_per_step": n_per_step, "note": "reference CPU path = " + what},
+        "cpu_baseline": {"value": value, "unit": "volumes/s", "cores": cores, "kind": kind, "sample": sample,
+                         "value_1_thread": one, "torch_config": torch.__config__.parallel_info().split("\n")[0:3]},
         "e2e": {"value": value, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -234,19 +276,85 @@ def gpu_step(cfg, x, idxs, out, step, group_offset=None):
     return Fn.salt_pepper(y, cfg["p"], seed=2024, offset=off, n_samples=B, mm=mm, out=y)
 
 
+def run_aux_workload(args):
+    """BASELINE.json configs[3] (2-D k-space spike on a stack of 8192 slices of 240 x 240) and configs[4] (chain-127 +
+    GibbsNoiseLayer on (B,1,128,128,64) crops) through the drop-in classes; every rank runs its own copy (weak scaling)."""
+    import torch.distributed as dist
+    rank, world, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the mvtb hot path has no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import filters_and_operators as F
+    import stylization_layers as S
+    from mvtb import _lib, functional as Fn
+    L = _lib.lib()
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    if args.workload == "cfg4":
+        x = torch.randn(8192, 240, 240, device=dev, generator=g)
+        t4 = F.KSpaceSpikeNoise((120 + 31, 120 - 17), 15.0)
+        step = lambda: t4(x)                                              # noqa: E731
+        units, unit, voxels, metric = 8192, "slices/s", x.numel(), "slices/sec (240x240 fp32)"
+        name = "cfg4: KSpaceSpikeNoise 2-D, one location for (8192,240,240) (F:982-983)"
+    else:
+        B = 32
+        x = torch.randn(B, 1, 128, 128, 64, device=dev, generator=g)
+        idxs = [(64 + (b % 5), 64 - (b % 7), 32 + (b % 3)) for b in range(B)]
+        layer = S.GibbsNoiseLayer(0.7)
+        step = lambda: layer(Fn.chain127(x, r=12.5, spike_idx=idxs, intensity=15.0, alpha=0.5, p=0.05, seed=7, sparse=True))   # noqa: E731
+        units, unit, voxels, metric = B, "volumes/s", 2 * x.numel(), "volumes/sec (128x128x64 fp32)"
+        name = "cfg5: chain-127 then GibbsNoiseLayer(0.7) on (32,1,128,128,64); two transforms = 16 B/voxel"
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)              # > L2, written between steps
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize(dev)
+        n0 = L.mvtb_launch_count()
+        tot = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step()
+            b.record()
+            torch.cuda.synchronize(dev)
+            tot += a.elapsed_time(b)
+        launches = int(L.mvtb_launch_count() - n0)
+    stats = torch.tensor([tot, float(units)], dtype=torch.float64, device=dev)
+    mx, sm = aggregate(stats, world)
+    if rank == 0:
+        ms = float(mx[0]) / args.steps
+        peak, peak_src = peak_hbm()
+        gbs = BYTES_PER_VOXEL * voxels / 2 ** 0 / (ms * 1e-3) / 1e9 if args.workload == "cfg4" else 8.0 * voxels / (ms * 1e-3) / 1e9
+        print(json.dumps({"metric": metric, "value": float(sm[1]) / (ms * 1e-3), "unit": unit, "n_gpus": world, "steps": args.steps,
+                          "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "f32", "data": "synthetic", "config": {"workload": name, "l2": "flushed between steps (256 MB written)"},
+                          "roofline_whole_step": {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+                                                  "note": "8 B/voxel per transform"},
+                          "gpu_launches": launches}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS) + list(AUX_WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default: the workload's)")
     ap.add_argument("--cpu-volumes", type=int, default=6, help="bounded CPU-baseline sample (volumes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (kernel sweeps)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle spot check printed in the JSON line")
     ap.add_argument("--disk-r", type=float, default=None, help="override the disk radius (sweeps; the headline uses the workload's 12.5)")
     args = ap.parse_args()
+    if args.workload in AUX_WORKLOADS:
+        return run_aux_workload(args)
     cfg = dict(WORKLOADS[args.workload])
     if args.batch:
         cfg["batch"] = args.batch
@@ -274,8 +382,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
 
+    strong = "strong_total" in cfg and not args.batch
+    if strong:                                         # strong scaling: the fixed total is split over the ranks
+        lo_s, hi_s = shard_range(cfg["strong_total"], rank, world)
+        cfg["batch"] = hi_s - lo_s
     B, C = cfg["batch"], cfg["channels"]
-    first = rank * B                                   # weak scaling: every rank owns its own B samples; seeds from the global index
+    first = lo_s if strong else rank * B               # weak scaling: every rank owns its own B samples; seeds from the global index
     x = make_inputs(cfg, first, dev)
     out = torch.empty_like(x)
     idxs = spike_indices(first, B) if cfg["spike"] else None
@@ -336,27 +448,30 @@ def main():
         b.record()
         torch.cuda.synchronize(dev)
         kernels["k_salt_pepper<philox>"] = {"launches_per_step": 1, "ms_per_step": a.elapsed_time(b) / 3, "avg_launch_ms": a.elapsed_time(b) / 3}
-    # roofline kernel = the most expensive HBM-bound kernel.  The in-place salt-and-pepper pass moves almost no
-    # algorithmic bytes (it stores only the selected voxels) and is bound by Philox instruction issue and
-    # scattered sector writes, so an HBM roofline fraction says nothing about it; it is listed in `kernels`
-    # and counted in roofline_whole_step.
-    hbm_kernels = {k: v for k, v in kernels.items() if not k.startswith("k_salt_pepper")} or kernels
-    dom = max(hbm_kernels, key=lambda k: hbm_kernels[k]["ms_per_step"]) if hbm_kernels else None
+    # roofline kernel = the most expensive kernel of the step.  Bytes it must move per voxel: the chain's
+    # 8 B/voxel are split between the kernel that reads the volume once and the one that writes it once; the
+    # intermediates they exchange are NF/H of a volume.  The whole-step figure below uses the full 8 B/voxel.
+    dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"]) if kernels else None
     peak, peak_src = peak_hbm()
     roofline = None
     if dom:
         kd = kernels[dom]
         vox = SHAPE[0] * SHAPE[1] * SHAPE[2]
         units_per_launch = vols_per_step / kd["launches_per_step"]
-        # Bytes this kernel must move per voxel.  The chain's 8 B/voxel are split
-        # between the kernel that reads the volume once and the one that writes it once; the intermediates
-        # they exchange are NF/H of a volume.  The whole-step figure below uses the full 8 B/voxel.
         nf = 13
-        own = {"k_bl_fwd_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_h": 4 + 8.0 * nf / SHAPE[0], "k_bl_inv_sp": 4 + 8.0 * nf / SHAPE[0],
-               "k_rows_fwd": 8.0, "k_rows_inv": 8.0, "k_axis<FWD>": 8.0, "k_axis<MID>": 8.0, "k_axis<INV>": 8.0,
-               "k_salt_pepper<philox>": 8.0 if cfg["p"] is None else 4.0 * cfg["p"]}.get(dom, 8.0)
-        # DRAM bytes per volume from the ncu --set full capture of this command (profiles/r01_ncu_full_final_selected_metrics.csv)
-        ncu_traffic = {"k_bl_fwd_h": 39.44e6, "k_bl_inv_h": 38.72e6, "k_salt_pepper<philox>": 23.76e6 if SPARSE_SP else 23.85e6}.get(dom)
+        half = 4 + 8.0 * nf / SHAPE[0]
+        own = {"k_bl_fwd_h": half, "k_bl_fwd_tc": half, "k_bl_inv_h": half, "k_bl_inv_sp": half,
+               "k_salt_pepper<philox>": 4.0 * (cfg["p"] or 0.0)}.get(dom, 8.0)
+        # DRAM bytes per volume of that kernel from the committed ncu capture of this command (profiles/r02_ncu_traffic.json,
+        # keyed by workload and kernel); null when no capture matches this configuration
+        ncu_traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                tr = json.load(f)
+            key = args.workload if args.disk_r is None and (FUSED_SP and SPARSE_SP) else None
+            ncu_traffic = tr.get(key, {}).get(dom) if key else None
+        except Exception:  # noqa: BLE001
+            ncu_traffic = None
         alg_bytes = own * vox * units_per_launch
         achieved = alg_bytes / (kd["avg_launch_ms"] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -364,9 +479,7 @@ def main():
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                     "algorithmic_bytes_per_voxel_this_kernel": own,
                     "share_of_step": kd["ms_per_step"] / sum(v["ms_per_step"] for v in kernels.values()),
-                    "most_expensive_kernel_overall": max(kernels, key=lambda k: kernels[k]["ms_per_step"]),
-                    "chain_bytes_per_voxel": BYTES_PER_VOXEL,
-                    "chain_equivalent_frac": (BYTES_PER_VOXEL * vox * units_per_launch / (kd["avg_launch_ms"] * 1e-3) / 1e9) / peak}
+                    "chain_bytes_per_voxel": BYTES_PER_VOXEL}
 
     # ---- end to end through the public API with host buffers: every step copies the batch from pinned host
     # memory, runs the chain, and copies the result back.  The batch moves in slices so that the H2D copy of
@@ -377,12 +490,13 @@ def main():
     from mvtb import hostmem
     affinity0 = os.sched_getaffinity(0)
     numa = hostmem.bind_to_gpu_numa_node(local_rank)           # pinned pages are first-touched on the GPU's node
-    hx = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
-    hx.copy_(x)
-    hy = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
-    xd = torch.empty_like(x)                                   # device staging, transformed in place
-    n_slices = 8 if B % 8 == 0 else (4 if B % 4 == 0 else 1)
-    sl = B // n_slices
+    Be = B if B * C <= 64 else max(1, 64 // C)                 # the host-buffer leg moves at most 64 volumes (2.3 GB each way) per step
+    hx = torch.empty((Be,) + tuple(x.shape[1:]), dtype=torch.float32, pin_memory=True)
+    hx.copy_(x[:Be])
+    hy = torch.empty(hx.shape, dtype=torch.float32, pin_memory=True)
+    xd = torch.empty((Be,) + tuple(x.shape[1:]), dtype=torch.float32, device=dev)     # device staging, transformed in place
+    n_slices = 8 if Be % 8 == 0 else (4 if Be % 4 == 0 else 1)
+    sl = Be // n_slices
     main = torch.cuda.current_stream(dev)
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ev_in = [torch.cuda.Event() for _ in range(n_slices)]
@@ -390,7 +504,7 @@ def main():
     ev_out = [torch.cuda.Event() for _ in range(n_slices)]
     groups_per_slice = sl * C * SHAPE[0] * SHAPE[1] * SHAPE[2] // 4
 
-    def e2e_step(s):
+    def e2e_step(s, compute=True):
         for i in range(n_slices):
             lo_, hi_ = i * sl, (i + 1) * sl
             with torch.cuda.stream(s_in):
@@ -398,8 +512,9 @@ def main():
                 xd[lo_:hi_].copy_(hx[lo_:hi_], non_blocking=True)
                 ev_in[i].record(s_in)
             main.wait_event(ev_in[i])
-            gpu_step(cfg, xd[lo_:hi_], None if idxs is None else idxs[lo_:hi_], xd[lo_:hi_], 300 + s,
-                     group_offset=(300 + s) * n_slices * groups_per_slice + i * groups_per_slice)
+            if compute:
+                gpu_step(cfg, xd[lo_:hi_], None if idxs is None else idxs[lo_:hi_], xd[lo_:hi_], 300 + s,
+                         group_offset=(300 + s) * n_slices * groups_per_slice + i * groups_per_slice)
             ev_done[i].record(main)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[i])
@@ -423,20 +538,52 @@ def main():
         e2e_checksum = float(hy.double().sum())
     os.sched_setaffinity(0, affinity0)
 
+    # ---- raw ceiling of the host link for this step's traffic: the same pinned buffers, H2D and D2H at once on two
+    # streams, no kernels (what e2e could reach if the chain were free)
+    ceiling_ms = float("nan")
+    if e2e_steps:
+        e2e_step(0, compute=False)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        c0.record()
+        for s_ in range(5):
+            e2e_step(s_ + 1, compute=False)
+        c1.record()
+        barrier()
+        ceiling_ms = c0.elapsed_time(c1) / 5
+
+    # ---- parity spot check, outside every timed region: sample 0 of this rank's batch through the same calls against
+    # the oracle (float64 exact-phase chain for the k-space part; SaltAndPepper on the coordinates the kernel hit)
+    parity = None
+    if rank == 0 and args.workload == "cfg2" and not args.no_parity:
+        from oracle import ref_port as P
+        x0 = x[0:1]
+        y3 = gpu_step(dict(cfg, p=None), x0, idxs[0:1], torch.empty_like(x0), 0)
+        y4 = gpu_step(cfg, x0, idxs[0:1], torch.empty_like(x0), 0)
+        torch.cuda.synchronize(dev)
+        a3, a4 = y3[0].cpu(), y4[0].cpu()
+        ref3 = P.chain_127_exact_phase(x0[0].cpu(), cfg["r"], idxs[0], 15.0, cfg["alpha"]).to(torch.float32)
+        hit = a4 != a3
+        u = torch.ones_like(a3)
+        u[hit] = torch.where(a4[hit] == a3.min() / 2, torch.tensor(cfg["p"] / 4), torch.tensor(3 * cfg["p"] / 4))
+        parity = {"kspace_rel_l2_vs_fp64_oracle": float((a3 - ref3).norm() / ref3.norm()), "tolerance": 1e-5,
+                  "select_equals_oracle_on_its_coordinates": bool(torch.equal(P.salt_and_pepper(a3, cfg["p"], u), a4)),
+                  "select_rate": float(hit.float().mean()), "sample": "sample 0 of rank 0, same library calls as the timed step"}
+
     # ---- max over ranks, whole-job aggregate; NCCL only gathers statistics
-    stats = torch.tensor([ms, e2e_ms, float(B), checksum], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms, e2e_ms, float(B), checksum, ceiling_ms, float(Be)], dtype=torch.float64, device=dev)
     mx, sm = aggregate(stats, world)
-    ms, e2e_ms = float(mx[0]), float(mx[1])
-    total_vols_per_step, checksum = float(sm[2]), float(sm[3])
+    ms, e2e_ms, ceiling_ms = float(mx[0]), float(mx[1]), float(mx[4])
+    total_vols_per_step, checksum, total_e2e_per_step = float(sm[2]), float(sm[3]), float(sm[5])
 
     if rank == 0:
         value = total_vols_per_step * args.steps / (ms * 1e-3)
-        e2e_value = total_vols_per_step * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
+        e2e_value = total_e2e_per_step * e2e_steps / (e2e_ms * 1e-3) if e2e_steps else None
         step_bytes = BYTES_PER_VOXEL * voxels
         line = {
             "metric": "volumes/sec (240x240x155 fp32)", "value": value, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {cfg['name']}", "volume": "%dx240x240x155" % C, "samples_per_gpu": B,
                        "volumes_per_step_per_gpu": vols_per_step, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs larger than L2 (%.2f GB in + out per step per GPU)" % (2 * voxels * 4 / 1e9),
@@ -447,18 +594,27 @@ def main():
                                     "frac": (step_bytes / (ms / args.steps * 1e-3) / 1e9) / peak,
                                     "note": "8 B/voxel x voxels per step / step time: the figure the 60% target refers to"},
             "kernels": kernels,
-            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(voxels * 4), "d2h_bytes_per_step": int(voxels * 4),
-                    "steps": e2e_steps, "slices_per_step": n_slices, "checksum": e2e_checksum, "numa_rank0": numa},
+            "e2e": {"value": e2e_value, "unit": "volumes/s", "h2d_bytes_per_step": int(hx.numel() * 4), "d2h_bytes_per_step": int(hx.numel() * 4),
+                    "samples_per_step_per_gpu": Be,
+                    "steps": e2e_steps, "slices_per_step": n_slices, "checksum": e2e_checksum, "numa_rank0": numa,
+                    "host_link_ceiling": None if not e2e_steps else {
+                        "value": total_e2e_per_step / (ceiling_ms * 1e-3), "unit": "volumes/s",
+                        "GBps_each_way_per_gpu": hx.numel() * 4 / (ceiling_ms * 1e-3) / 1e9,
+                        "how": "the e2e step with the library calls left out: the same slices copied H2D and D2H on the same streams and events, max over ranks",
+                        "e2e_frac_of_ceiling": (e2e_value or 0.0) / (total_e2e_per_step / (ceiling_ms * 1e-3))}},
+            "parity_spot_check": parity,
             "gpu_launches": launches,
             "clocks": clocks,
             "checksum": checksum,
         }
         if not args.no_cpu_baseline and world >= 1:
             nv = max(1, args.cpu_volumes // (C * C))
-            v, cores, ts = time_cpu_reference(cfg, nv)
-            line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": cores, "kind": "port",
-                                    "sample": f"{nv} sample(s) of {C}x240x240x155 through oracle/ref_port.py (same torch op sequence as the reference), "
-                                              f"{cores} threads, {sum(ts):.1f} s"}
+            v, cores, ts, v1, kind = time_cpu_reference(cfg, nv)
+            src = ("the unmodified reference classes (oracle/_ref through oracle/monai_shim)" if kind == "reference"
+                   else "oracle/ref_port.py (same torch op sequence as the reference)")
+            line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": cores, "kind": kind, "value_1_thread": v1,
+                                    "sample": f"{nv} sample(s) of {C}x240x240x155 through {src}, {cores} threads, {sum(ts):.1f} s; "
+                                              f"1 more on one thread"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

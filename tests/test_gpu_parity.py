@@ -34,7 +34,7 @@ def t(a):
 def test_extension_is_the_thing_running(cuda_device):
     """The CUDA library is loaded and the transforms produce CUDA-side results (no silent fallback)."""
     from mvtb import _lib, functional as Fn
-    assert _lib.lib().mvtb_version() == 100
+    assert _lib.lib().mvtb_version() >= 200
     x = torch.randn(1, 8, 8, 8, device=cuda_device)
     mm = Fn.minmax(x)
     assert mm.is_cuda and float(mm[0, 0]) == float(x.min()) and float(mm[0, 1]) == float(x.max())

@@ -282,4 +282,4 @@ def test_bench_reference_arm_json_contract():
     assert line["config"]["workload"].startswith("cfg2")
     assert line["e2e"] == {"value": line["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+    assert cb["kind"] in ("reference", "port") and cb["value_1_thread"] > 0 and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
