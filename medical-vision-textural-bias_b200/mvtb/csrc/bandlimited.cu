@@ -747,6 +747,14 @@ static void is_build_pattern(int A, int B, int lag, int spread, std::vector<unsi
     *max_back = mb;
 }
 
+// shared memory of the fused W/D kernel: the [K][K] bins share the front of the buffer with the W table
+template <int NF>
+static size_t bl_midw_smem(const BlGeom& g, int K) {
+    const size_t smem_w = sizeof(float) * (size_t)(g.W / 2 + 1) * BlDims<NF>::NT;
+    const size_t bins = sizeof(cf) * (size_t)K * K;
+    return ((smem_w > bins ? smem_w : bins) + 15) / 16 * 16 + sizeof(cf) * ((size_t)K * g.D + g.D);
+}
+
 template <int NF>
 static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, const mvtb_chain_desc* desc, int n_desc,
                   int F, float* minmax_out, int vols_per_sample, void* stream, SpFuse* sp, const float* pre_abt) {
@@ -769,11 +777,13 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         int rc = bl_make_vol(p, g, desc[i], &hv[i]);
         if (rc != MVTB_OK) return rc;
     }
-    // ... followed by the [K][D] D-axis twiddle table of the mid kernel
+    // ... followed, only when the three-kernel W/D stage will run, by the [K][D] D-axis twiddle table of k_bl_mid
+    // (3 875 double-precision sincos on the host for r = 12.5: ~0.1 ms per call that the fused W/D kernel never reads)
     const size_t vol_bytes = (hv.size() * sizeof(BlVol) + 15) & ~(size_t)15;
-    std::vector<unsigned char> hbuf(vol_bytes + sizeof(cf) * (size_t)K * g.D);
+    const bool split_mid = !p->opt_fusemid || bl_midw_smem<NF>(g, K) > (size_t)113 * 1024;
+    std::vector<unsigned char> hbuf(vol_bytes + (split_mid ? sizeof(cf) * (size_t)K * g.D : 0));
     memcpy(hbuf.data(), hv.data(), hv.size() * sizeof(BlVol));
-    {
+    if (split_mid) {
         cf* tw = (cf*)(hbuf.data() + vol_bytes);
         for (int jd = 0; jd < K; ++jd)
             for (int d = 0; d < g.D; ++d) {
@@ -970,9 +980,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
             }
         }
-        const size_t bins = sizeof(cf) * (size_t)K * K;                      // shares the front of the buffer with the W table
-        const size_t smem_mw = ((smem_w > bins ? smem_w : bins) + 15) / 16 * 16 + sizeof(cf) * ((size_t)K * g.D + g.D);
-        if (smem_mw <= 113 * 1024 && p->opt_fusemid) {                      // at least 2 CTAs per SM
+        const size_t smem_mw = bl_midw_smem<NF>(g, K);
+        if (!split_mid) {                                                   // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);
             auto kern = k_bl_midw<NF>;
