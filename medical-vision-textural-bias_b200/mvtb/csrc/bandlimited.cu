@@ -892,17 +892,21 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         bool tc_fwd = false;
 #ifndef MVTB_EMU
         const int tcN = (2 * NF + 15) / 16 * 16;
-        // TMA boxes: k stages of 16 rows per copy, k the largest divisor of H / 16 with at most 64 rows; ring as deep as
-        // ~128 KB (and the table) allow, at most kTcRawStages stages
-        int tc_bs = 1;
-        for (int k = 1; k <= 4; ++k)
-            if ((g.H / kTcRows) % k == 0) tc_bs = k;
+        // TMA boxes / A-operand slots of k stages of 16 rows, k the largest divisor of H / 16 up to kTcMaxBoxStages whose
+        // slots (32 k TMEM columns each, at least two) fit beside the six accumulators; the raw ring takes what shared
+        // memory is left next to the table, at most kTcMaxRing boxes
+        int tc_bs = 1, tc_slots = 0;
+        for (int k = 1; k <= kTcMaxBoxStages; ++k)
+            if ((g.H / kTcRows) % k == 0 && 6 * tcN + 2 * 32 * k <= 512) tc_bs = k;
+        tc_slots = (512 - 6 * tcN) / (32 * tc_bs);
+        if (tc_slots > kTcMaxSlots) tc_slots = kTcMaxSlots;
         const size_t tc_tab = ((size_t)2 * g.H * tcN * sizeof(float) + 1023) & ~(size_t)1023;
-        int tc_ring = (int)(((size_t)200 * 1024 - tc_tab) / ((size_t)tc_bs * kTcRows * 128 * sizeof(float)));
-        if (tc_ring * tc_bs > kTcRawStages) tc_ring = kTcRawStages / tc_bs;
+        int tc_ring = (int)(((size_t)220 * 1024 - tc_tab) / ((size_t)tc_bs * kTcRows * 128 * sizeof(float)));
+        if (tc_ring > kTcMaxRing) tc_ring = kTcMaxRing;
+        if (tc_slots > 0) tc_ring -= tc_ring % tc_slots;          // a multiple of the converter groups (= slots): see the kernel
         const size_t smem_tc = tc_tab + (size_t)tc_ring * tc_bs * kTcRows * 128 * sizeof(float);
         tc_fwd = p->opt_tc && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
-                 tc_ring >= 2 && g.NC * (long long)g.H < 0x7fffffffLL;
+                 tc_ring >= 2 && tc_slots >= 2 && g.NC * (long long)g.H < 0x7fffffffLL;
 #endif
         {
             ProfScope prof(p, tc_fwd ? MVTB_K_BL_FWD_TC : MVTB_K_BL_FWD_H, stream);
@@ -920,7 +924,6 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 }
                 int rcm = tc_make_tmap(&tmap, src, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, tc_bs * kTcRows);
                 if (rcm != MVTB_OK) return rcm;
-                ta.x = src;
                 ta.Y = Y;
                 int rct = tc_fwd_table(p, NF, tcN, &ta.tab);
                 if (rct != MVTB_OK) return rct;
@@ -929,6 +932,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 ta.n_tiles = ta.tiles_per_vol * nv;
                 ta.box_stages = tc_bs;
                 ta.ring_boxes = tc_ring;
+                ta.a_slots = tc_slots;
                 ta.status = p->tc_status;
                 ta.prof = nullptr;
                 if (getenv("MVTB_TC_PROF")) {                  // measurements: waits and an event timeline of CTA 0, printed at the next call
@@ -940,20 +944,13 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                         MVTB_CUDA(cudaMemcpy(h.data(), dprof, np * sizeof(long long), cudaMemcpyDeviceToHost));
                         fprintf(stderr, "k_bl_fwd_tc CTA 0: total %lld cycles; waits by warp (codes 1..7):", h[0]);
                         for (int w = 0; w < 27; ++w) { fprintf(stderr, "\n  warp %2d:", w); for (int c = 1; c < 8; ++c) fprintf(stderr, " %10lld", h[w * 8 + c]); }
-                        fprintf(stderr, "\nTRACE");
-                        for (int w = 0; w < 27; ++w)
-                            for (int i = 0; i < 64; ++i) {
-                                const long long e = h[256 + w * 64 + i];
-                                if (e) fprintf(stderr, "\nT %d %d %d %lld", w, (int)(e >> 56), (int)((e >> 40) & 0xffff), e & 0xffffffffffLL);
-                            }
-                        fprintf(stderr, "\nENDTRACE\n");
+                        fprintf(stderr, "\n");
                     }
                     MVTB_CUDA(cudaMemset(dprof, 0, np * sizeof(long long)));
                     ta.prof = dprof;
                 }
                 const unsigned grid = (unsigned)(ta.n_tiles < p->num_sms ? ta.n_tiles : p->num_sms);
-                if (p->tc_tma) MVTB_LAUNCH(k_bl_fwd_tc<true>, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
-                else MVTB_LAUNCH(k_bl_fwd_tc<false>, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
+                MVTB_LAUNCH(k_bl_fwd_tc, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
             } else
 #endif
             {
@@ -1095,8 +1092,7 @@ int configure_bl_kernels(const mvtb_plan* p) {
     if ((rc = bl_configure_nf<26>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_configure_nf<32>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_mid, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_tc<true>, optin)) != MVTB_OK) return rc;
-    if ((rc = bl_big_smem(k_bl_fwd_tc<false>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_fwd_tc, optin)) != MVTB_OK) return rc;
 #endif
     (void)p;
     return MVTB_OK;
