@@ -6,12 +6,12 @@
 // 3xTF32 split  x*T ~ xh*Th + xl*Th + xh*Tl  (xh = tf32(x), xl = tf32(x - xh); rel-L2 ~1e-6, measured by
 // tools/tc_probe.cu), and the SM's threads only convert and move data:
 //
-//   producer   (1 thread)   1-D bulk copies (cp.async.bulk, UBLKCP) of 16 rows x 128 columns of x into a ring of raw
-//                           shared-memory stages, completion counted in bytes on an mbarrier
-//   converters (8 warps)    thread = (column, half of the 16 rows): LDS, split into (hi, lo), tcgen05.st into a ring
-//                           of A-operand slots in TMEM (lane = column, one 32-bit TMEM column per h)
-//   MMA issuer (1 thread)   per 8 rows: D += A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, A from TMEM, B (the cos / -sin table,
-//                           split on the host) from shared memory; tcgen05.commit frees the A slot
+//   producer   (1 warp)     2-D TMA boxes (cp.async.bulk.tensor, UTMALDG) of 16 `box_stages` rows x 128 columns of x into a
+//                           ring in shared memory, completion counted in bytes on an mbarrier
+//   converters (<= 16 warps) thread = column: LDS, split into (hi, lo), tcgen05.st into a ring of A-operand slots in
+//                           TMEM (lane = column, one 32-bit TMEM column per h); one group of 4 warps per slot
+//   MMA issuers (6 warps)   (tile parity, term): per 8 rows D_term += A_hi*B_hi | A_lo*B_hi | A_hi*B_lo, A from TMEM, B (the
+//                           cos / -sin table, split on the host) from shared memory; tcgen05.commit frees the A slot
 //   epilogue   (4 warps)    tcgen05.ld of the finished 128 x N accumulator, coalesced 8-byte stores into Y[f][col]
 //
 // All hand-offs are mbarriers; every wait is bounded (a protocol bug sets *status instead of hanging the GPU).
@@ -26,7 +26,8 @@ static const int kTcMaxBoxStages = 4;   // stages per TMA box (= per A-operand s
 static const int kTcMaxRing = 8;        // boxes in the raw shared-memory ring, at most
 static const int kTcMaxSlots = 4;       // A-operand slots in TMEM, at most
 static const int kTcConvGroups = 4;     // converter groups of 4 warps (one per TMEM lane quarter), at most; a.a_slots of them work
-static const int kTcIssuers = 6;        // MMA-issuing warps: (3xTF32 term, K-step of a stage), each with its own accumulator
+static const int kTcIssuers = 6;        // MMA-issuing warps: (tile parity, 3xTF32 term), each with its own accumulator
+static const int kTcTerms = 3;          // issuers (and accumulators) per tile
 static const int kTcWarpIss0 = 1, kTcWarpEpi0 = 1 + kTcIssuers, kTcWarpConv0 = kTcWarpEpi0 + 4;
 static const int kTcFwdThreads = 32 * (kTcWarpConv0 + 4 * kTcConvGroups);
 
@@ -45,7 +46,7 @@ struct TcFwdArgs {
 struct TcBars {
     unsigned long long raw_full[kTcMaxRing], raw_empty[kTcMaxRing];
     unsigned long long a_full[kTcMaxSlots], a_empty[kTcMaxSlots];
-    unsigned long long d_full, d_empty;
+    unsigned long long d_full[2], d_empty[2];    // per tile parity: the accumulators are double-buffered
 };
 
 // bounded wait that also gives up when another role has failed
@@ -77,9 +78,12 @@ __device__ __forceinline__ bool tc_wait(unsigned long long* bar, uint32_t parity
 
 // What the measurements on a B200 dictated (tools/tc_rate.cu, tc_rate2.cu, MVTB_TC_PROF; profiles/r02_tc_*):
 //  * one issuing warp pays ~105-125 cycles per tcgen05.mma whatever the tile (M = 64/128, N = 16..128, A from shared
-//    memory or TMEM), while the tensor pipe takes ~25 for 128 x 32 x 8: six warps issue, one per (3xTF32 term, K-step),
-//    each into its own accumulator; the epilogue adds the six.  A lone `if (lane == 0)` issuer costs ~200 (ptxas wraps
+//    memory or TMEM), while the tensor pipe takes ~25 for 128 x 32 x 8: several warps issue, one per 3xTF32 term, each
+//    into its own accumulator; the epilogue adds them.  A lone `if (lane == 0)` issuer costs ~200 (ptxas wraps
 //    every UTCMMA in an ELECT / BRA.U.ANY loop): the whole warp runs the loop and one elected lane issues.
+//  * with ONE set of accumulators the issuers sat 40 % of the kernel waiting for the epilogue to drain the previous
+//    tile (MVTB_TC_PROF: 3.1 k of 7.6 k cycles per tile): two sets of three issuers take even / odd tiles, so the
+//    accumulators are double-buffered within the same 6 N columns of TMEM.
 //  * a copy costs its issuing thread ~90 cycles (1-D bulk) to ~550 (2-D tensor map) and lands ~2.9 k cycles later: one
 //    TMA box of several stages (24 KB for H = 240), five boxes deep.
 //  * every hand-off costs a wake-up (~100-400 cycles): the unit of work between roles is a box of `box_stages` stages
@@ -109,8 +113,7 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
         s_abort = 0;
         for (int i = 0; i < kTcMaxRing; ++i) { tc::mbar_init(tc::smem_u32(&bars.raw_full[i]), 1); tc::mbar_init(tc::smem_u32(&bars.raw_empty[i]), 4); }   // 4 = warps of the one group that reads the box
         for (int i = 0; i < kTcMaxSlots; ++i) { tc::mbar_init(tc::smem_u32(&bars.a_full[i]), 4); tc::mbar_init(tc::smem_u32(&bars.a_empty[i]), kTcIssuers); }
-        tc::mbar_init(tc::smem_u32(&bars.d_full), kTcIssuers);
-        tc::mbar_init(tc::smem_u32(&bars.d_empty), 4);
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tc::smem_u32(&bars.d_full[i]), kTcTerms); tc::mbar_init(tc::smem_u32(&bars.d_empty[i]), 4); }
         tc::mbar_init_fence();
     }
     const uint32_t tmem_cols = 512;
@@ -121,6 +124,7 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     volatile int* abortp = &s_abort;
+    const long long t_start = a.prof ? clock64() : 0;
 
     if (warp == 0) {
         // ------------------------------------------------------------ producer: one TMA box per slot of the raw ring
@@ -141,16 +145,29 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
             if (!ok) break;
         }
     } else if (warp < kTcWarpEpi0) {
-        // ------------------------------------------------------------ MMA issuers: `bs` MMAs and one commit per box
-        const int iss = warp - kTcWarpIss0, term = iss >> 1, ks = iss & 1;   // term 0 = hi*hi, 1 = lo*hi, 2 = hi*lo
+        // ------------------------------------------------------------ MMA issuers: 2 `bs` MMAs and one commit per box
+        const int iss = warp - kTcWarpIss0, set = iss / kTcTerms, term = iss - set * kTcTerms;   // term 0 = hi*hi, 1 = lo*hi, 2 = hi*lo
         const uint32_t idesc = tc::idesc_tf32(128, N);
         const uint32_t chunk_stride = (uint32_t)(N / 8) * 128u, group_stride = 128u;
         const uint32_t b0 = tc::smem_u32(term == 2 ? tab_lo : tab_hi);
-        const uint32_t a_off = (term == 1 ? 16u : 0u) + (uint32_t)ks * 8u;   // within a stage's 32 columns: [hi 16 | lo 16]
+        const uint32_t a_off = term == 1 ? 16u : 0u;                         // within a stage's 32 columns: [hi 16 | lo 16]
         const uint32_t d = tmem + d_col0 + (uint32_t)iss * (uint32_t)N;
         unsigned ib = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles && !*abortp; tile += gridDim.x, ++tcount) {
-            if (!tc_wait(&bars.d_empty, (tcount & 1) ^ 1, abortp, a.status, 2, a.prof)) break;
+            if ((int)(tcount & 1u) != set) {
+                // The other set's tile.  Still observe every fill and sign the slot off: a parity wait is only sound
+                // when the waiter is never a phase ahead of or behind its barrier, so all six issuers see all boxes.
+                bool ok = true;
+                for (int b = 0; b < n_box; ++b, ++ib) {
+                    const int sl = (int)(ib % (unsigned)a.a_slots);
+                    if (!tc_wait(&bars.a_full[sl], (ib / (unsigned)a.a_slots) & 1u, abortp, a.status, 7, a.prof)) { ok = false; break; }
+                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bars.a_empty[sl]));
+                    __syncwarp();
+                }
+                if (!ok) break;
+                continue;
+            }
+            if (!tc_wait(&bars.d_empty[set], ((tcount >> 1) & 1u) ^ 1u, abortp, a.status, 2, a.prof)) break;
             tc::fence_after_sync();
             uint32_t acc = 0;
             bool ok = true;
@@ -159,9 +176,9 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
                 if (!tc_wait(&bars.a_full[sl], (ib / (unsigned)a.a_slots) & 1u, abortp, a.status, 3, a.prof)) { ok = false; break; }
                 tc::fence_after_sync();
                 if (tc::elect_one()) {
-                    for (int k = 0; k < bs; ++k) {
-                        const uint32_t koff = (uint32_t)((b * bs + k) * (kTcRows / 8) + ks) * 2u * chunk_stride;
-                        tc::mma_ts(d, tmem + a_col0 + (uint32_t)sl * slot_cols + 32u * (uint32_t)k + a_off,
+                    for (int k = 0; k < 2 * bs; ++k) {                       // K-steps of 8 rows
+                        const uint32_t koff = (uint32_t)(b * bs * (kTcRows / 8) + k) * 2u * chunk_stride;
+                        tc::mma_ts(d, tmem + a_col0 + (uint32_t)sl * slot_cols + 32u * (uint32_t)(k >> 1) + a_off + 8u * (uint32_t)(k & 1),
                                    tc::smem_desc(b0 + koff, chunk_stride, group_stride), idesc, acc);
                         acc = 1;
                     }
@@ -171,41 +188,39 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
                 __syncwarp();
             }
             if (!ok) break;
-            if (tc::elect_one()) tc::mma_commit(tc::smem_u32(&bars.d_full));
+            if (tc::elect_one()) tc::mma_commit(tc::smem_u32(&bars.d_full[set]));
             __syncwarp();
         }
     } else if (warp < kTcWarpConv0) {
-        // ------------------------------------------------------------ epilogue: sum of the six accumulators -> Y[f][col]
+        // ------------------------------------------------------------ epilogue: sum of the tile's three accumulators -> Y[f][col]
         const int q = warp & 3;                                       // TMEM lanes 32 q .. 32 q + 31
         const int m = 32 * q + lane;
         unsigned tcount = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles && !*abortp; tile += gridDim.x, ++tcount) {
             const int vol = tile / a.tiles_per_vol, c0 = (tile - vol * a.tiles_per_vol) * 128;
-            if (!tc_wait(&bars.d_full, tcount & 1, abortp, a.status, 4, a.prof)) break;
+            const unsigned set = tcount & 1u;
+            if (!tc_wait(&bars.d_full[set], (tcount >> 1) & 1u, abortp, a.status, 4, a.prof)) break;
             tc::fence_after_sync();
             const bool okc = c0 + m < NC;
             float2* yv = a.Y + ((size_t)vol * a.NF) * NC + c0 + m;
-            const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + d_col0;
+            const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + d_col0 + set * (uint32_t)(kTcTerms * N);
             for (int c = 0; c < N / 8; ++c) {
-                uint32_t v[6][8];
+                uint32_t v[kTcTerms][8];
                 MVTB_UNROLL
-                for (int i = 0; i < 6; ++i) tc::tmem_ld8(t0 + (uint32_t)i * (uint32_t)N + 8u * c, v[i]);
+                for (int i = 0; i < kTcTerms; ++i) tc::tmem_ld8(t0 + (uint32_t)i * (uint32_t)N + 8u * c, v[i]);
                 tc::tmem_ld_wait();
                 if (c == N / 8 - 1) {                                // everything is in registers: release the accumulators
                     tc::fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bars.d_empty));
+                    if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bars.d_empty[set]));
                 }
                 MVTB_UNROLL
                 for (int j = 0; j < 4; ++j) {
                     const int f = 4 * c + j;
                     float r[2];
                     MVTB_UNROLL
-                    for (int e = 0; e < 2; ++e) {                     // small terms first, then the two hi*hi halves
-                        const float sm = (__uint_as_float(v[2][2 * j + e]) + __uint_as_float(v[3][2 * j + e])) +
-                                         (__uint_as_float(v[4][2 * j + e]) + __uint_as_float(v[5][2 * j + e]));
-                        r[e] = sm + (__uint_as_float(v[0][2 * j + e]) + __uint_as_float(v[1][2 * j + e]));
-                    }
+                    for (int e = 0; e < 2; ++e)                       // small terms first, then hi*hi
+                        r[e] = (__uint_as_float(v[1][2 * j + e]) + __uint_as_float(v[2][2 * j + e])) + __uint_as_float(v[0][2 * j + e]);
                     if (okc && f < a.NF) yv[(size_t)f * NC] = make_float2(r[0], r[1]);
                 }
             }
@@ -251,6 +266,7 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
     }
     tc::fence_before_sync();
     __syncthreads();
+    if (a.prof && blockIdx.x == 0 && tid == 0) a.prof[0] = clock64() - t_start;
     if (warp == 1) tc::tmem_dealloc(tmem, tmem_cols);
 }
 #endif  // MVTB_EMU
