@@ -216,7 +216,9 @@ int mvtb_wrap_odd_last_f32(mvtb_plan* plan, const float* in, float* out, int n_v
 #define MVTB_K_BL_INV_SP 13
 #define MVTB_K_BL_FWD_TC 14
 #define MVTB_K_BL_INV_TC 15
-#define MVTB_K_KINDS 16
+#define MVTB_K_BL_MM_TC 16     /* k_bl_inv_tc<NF, 0>: compute-only pass, per-sample (min, max) */
+#define MVTB_K_SP_BITS 17      /* k_sp_bits: the select pass's coordinates as 2 bits per voxel */
+#define MVTB_K_KINDS 18
 int mvtb_plan_profile(mvtb_plan* plan, int enable);   /* 1: reset + start recording, 0: stop */
 /* synchronises the recorded events; fills ms_sum[kind] / counts[kind] (arrays of MVTB_K_KINDS) */
 int mvtb_plan_profile_read(mvtb_plan* plan, double* ms_sum, int* counts);
@@ -231,8 +233,9 @@ unsigned long long mvtb_launch_count(void);           /* kernels launched by thi
 #define MVTB_PATH_BL_PAIRS 2   /* automatic, but the band-limited H kernels use pair folding even when H % 4 == 0 */
 #define MVTB_PATH_BL_SPLIT 3   /* automatic, but the band-limited W axis, D axis and pointwise stage run as three kernels */
 int mvtb_plan_set_path(mvtb_plan* plan, int path);
-#define MVTB_PATH_BL_CUDACORE 4 /* automatic, with the band-limited H-axis forward pass on the CUDA cores (the default today) */
-#define MVTB_PATH_BL_TC 5       /* automatic, with the band-limited H-axis forward pass on the tensor cores (tcgen05, 3xTF32) */
+#define MVTB_PATH_BL_CUDACORE 4 /* automatic, with both band-limited H-axis passes on the CUDA cores */
+#define MVTB_PATH_BL_TC 5       /* automatic, with both band-limited H-axis passes on the tensor cores (tcgen05, 3xTF32); AUTO runs
+                                   the forward pass there (faster) and the inverse pass on the CUDA cores (MVTB_TC / MVTB_TC_INV) */
 
 /* Synchronises the device and returns 0, or a positive code if a tensor-core kernel of this plan gave up on one of
  * its (bounded) mbarrier waits -- a protocol bug; results of that call are then invalid.  For tests. */

@@ -82,7 +82,7 @@ _SYMBOLS = {
     "mvtb_plan_set_path": (C.c_int, [C.c_void_p, C.c_int]),
     "mvtb_plan_tc_status": (C.c_int, [C.c_void_p]),
 }
-K_KINDS = 16
+K_KINDS = 18
 SP_BLOCK = 256
 
 

@@ -563,6 +563,7 @@ k_bl_inv_h(const cf* __restrict__ Y, float* __restrict__ out, BlGeom g, int n_cb
 #include "bandlimited_quad.cuh"
 #include "bandlimited_sp.cuh"
 #include "bandlimited_tc.cuh"
+#include "bandlimited_tci.cuh"
 
 // ------------------------------------------------------------------ host side
 size_t bl_workspace_per_volume(const mvtb_plan* p, int F);
@@ -721,6 +722,37 @@ static int tc_fwd_table(mvtb_plan* p, int NF, int N, const float** out) {
     *out = p->tc_tab_fwd[slot];
     return MVTB_OK;
 }
+// B operand of the inverse pass (bandlimited_tci.cuh), [2][K * H] (hi, lo) in tc::op_offset(row = h, k, rows = H) order:
+// column 2f = c_f cos(2 pi f h / H), 2f+1 = -c_f sin(2 pi f h / H), c_0 = 1, c_f = 2; the plane-wave columns
+// (k >= 2 NF) are zero here and written per volume by the kernel
+static int tc_inv_table(mvtb_plan* p, int NF, int K, const float** out) {
+    const int slot = nf_slot(NF);
+    if (slot < 0) return MVTB_EUNSUPPORTED;
+    if (!p->tc_tab_inv[slot]) {
+        const int H = p->shape[2];
+        std::vector<float> t((size_t)2 * H * K, 0.f);
+        for (int k = 0; k < 2 * NF; ++k)
+            for (int h = 0; h < H; ++h) {
+                const int f = k / 2;
+                const long long m = ((long long)f * h) % H;
+                const double ang = 2.0 * M_PI * (double)m / (double)H;
+                const double cfw = f == 0 ? 1.0 : 2.0;
+                const double v = (k & 1) ? -cfw * sin(ang) : cfw * cos(ang);
+                const float hi = tf32_round((float)v), lo = tf32_round((float)(v - (double)hi));
+                const size_t o = tc::op_offset(h, k, H) / 4;
+                t[o] = hi;
+                t[(size_t)H * K + o] = lo;
+            }
+        MVTB_CUDA(cudaMalloc((void**)&p->tc_tab_inv[slot], t.size() * sizeof(float)));
+        MVTB_CUDA(cudaMemcpy(p->tc_tab_inv[slot], t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if (!p->tc_status) {
+        MVTB_CUDA(cudaMalloc((void**)&p->tc_status, sizeof(int)));
+        MVTB_CUDA(cudaMemset(p->tc_status, 0, sizeof(int)));
+    }
+    *out = p->tc_tab_inv[slot];
+    return MVTB_OK;
+}
 #endif
 
 // One period of the fused kernel's work queue (bandlimited_sp.cuh): the A inverse tiles of a sample at times
@@ -811,6 +843,27 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 // the select pass must find its sample in L2: beyond ~1.5 samples of 36 MB the lines are gone (tools/l2probe.cu)
                 // and the separate pass is faster (4-channel BraTS samples of 143 MB: 9.4 k vs 8.9 k samples/s)
                 (size_t)vps * p->vol_real * sizeof(float) <= ((size_t)p->is_max_sample_mb << 20);
+    // ---- tensor-core inverse pass (bandlimited_tci.cuh), with the select pass folded into its stores when asked for
+    bool tc_inv = false, tc_sel = false;
+    size_t smem_tci = 0, smem_bits = 0;
+    int tci_stages = 2;
+    unsigned long long tc_bps = 0;
+#ifndef MVTB_EMU
+    {
+        constexpr int KT = TciDims<NF>::K;
+        // B (hi, lo) + four A stages (hi, lo) when they fit, else two
+        const size_t tci_pwt = 0;
+        tci_stages = sizeof(float) * ((size_t)2 * KT * g.H + (size_t)8 * 128 * KT) + tci_pwt <= (size_t)220 * 1024 ? 4 : 2;
+        smem_tci = sizeof(float) * ((size_t)2 * KT * g.H + (size_t)tci_stages * 2 * 128 * KT) + tci_pwt;
+        smem_bits = (size_t)((g.NC + 3) / 4) * 16;
+        tc_inv = p->opt_tc && p->opt_tc_inv && g.H % kTciRowsPerWord == 0 && g.H >= 16 && g.H <= 256 && smem_tci <= (size_t)220 * 1024 &&
+                 g.NC * (long long)g.H < 0x7fffffffLL && nf_slot(NF) >= 0;
+        tc_bps = ((unsigned long long)vps * p->vol_real + MVTB_SP_SPAN - 1) / MVTB_SP_SPAN;
+        tc_sel = tc_inv && sp != nullptr && sp->p > 0.f && minmax_out != nullptr && vps >= 1 && vps <= kBlChunk &&
+                 n_volumes % vps == 0 && smem_bits <= (size_t)200 * 1024 && tc_bps <= 0x7fffffffull;
+        if (tc_inv) fuse = false;
+    }
+#endif
     IsArgs ia;
     memset(&ia, 0, sizeof(ia));
     std::vector<unsigned> pattern;
@@ -843,6 +896,13 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             ia.minmax = minmax_out;
             ia.debug = getenv("MVTB_IS_DEBUG") ? atoi(getenv("MVTB_IS_DEBUG")) : 0;
         }
+    }
+    if (tc_sel) {
+        chunk -= chunk % vps;                             // whole samples per launch
+        tab_off = hbuf.size();
+        hbuf.resize(tab_off + sizeof(unsigned) * MVTB_SP_BLOCK);
+        int rct = mvtb_sparse_table(sp->p, (unsigned*)(hbuf.data() + tab_off));
+        if (rct != MVTB_OK) return rct;
     }
     if (fuse) {
         pat_off = hbuf.size();
@@ -889,6 +949,39 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         // chunk mapped into its output slot first (the inverse pass overwrites that slot only after the forward pass)
         const float* src = in + (size_t)v0 * p->vol_real;
         const float* abt_v = pre_abt ? pre_abt + (size_t)3 * v0 : nullptr;
+        // the select pass's (hit, coin) bits of this chunk: data-independent, so the kernel can run on the plan's side
+        // stream next to the W/D stage (a k_sp_bits CTA and a k_bl_midw CTA fit one SM together), joined before the
+        // store pass; or in line when the overlap is off
+        bool bits_launched = false;
+        auto launch_bits = [&](void* st) -> int {
+#ifndef MVTB_EMU
+            const int RG = g.H / kTciRowsPerWord;
+            const size_t need = sizeof(unsigned) * (size_t)chunk * RG * (size_t)g.NC;
+            if (p->tc_bits_bytes < need) {
+                if (p->tc_bits) cudaFree(p->tc_bits);
+                p->tc_bits = nullptr;
+                p->tc_bits_bytes = 0;
+                MVTB_CUDA(cudaMalloc((void**)&p->tc_bits, need));
+                p->tc_bits_bytes = need;
+            }
+            ProfScope prof(p, MVTB_K_SP_BITS, st);
+            SpBitsArgs sa;
+            sa.bits = p->tc_bits;
+            sa.H = g.H; sa.NC = (int)g.NC; sa.vps = vps; sa.RG = RG;
+            sa.vol_n = (unsigned long long)p->vol_real;
+            sa.n_per_sample = (unsigned long long)vps * p->vol_real;
+            sa.bps = (unsigned)tc_bps;
+            sa.s_base = v0 / vps;
+            sa.table = (const unsigned*)((const unsigned char*)dvp + tab_off);
+            const double l2q = log2(1.0 - (double)sp->p);
+            sa.inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
+            sa.seed = sp->seed;
+            sa.offset = sp->offset;
+            MVTB_LAUNCH(k_sp_bits, dim3((unsigned)(nv * RG)), dim3(1024), smem_bits, st, sa);
+#endif
+            (void)st;
+            return MVTB_OK;
+        };
         bool tc_fwd = false;
 #ifndef MVTB_EMU
         const int tcN = (2 * NF + 15) / 16 * 16;
@@ -977,6 +1070,23 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
             }
         }
+#ifndef MVTB_EMU
+        if (tc_sel && p->opt_bits_overlap) {
+            if (!p->side_stream) {
+                MVTB_CUDA(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
+                MVTB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+                MVTB_CUDA(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+            }
+            // after the forward pass (whose CTAs fill shared memory: nothing fits next to them), and after the previous
+            // chunk's store pass, which read the same buffer
+            MVTB_CUDA(cudaEventRecord(p->ev_fork, (cudaStream_t)stream));
+            MVTB_CUDA(cudaStreamWaitEvent(p->side_stream, p->ev_fork, 0));
+            int rcb = launch_bits((void*)p->side_stream);
+            if (rcb != MVTB_OK) return rcb;
+            MVTB_CUDA(cudaEventRecord(p->ev_join, p->side_stream));
+            bits_launched = true;
+        }
+#endif
         const size_t smem_mw = bl_midw_smem<NF>(g, K);
         if (!split_mid) {                                                   // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
@@ -999,6 +1109,80 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 MVTB_LAUNCH(kern, dim3((unsigned)(n_tblocks * nv)), dim3(kWThreads), smem_w, stream, (const cf*)G, Y, g, n_tblocks);
             }
         }
+#ifndef MVTB_EMU
+        if (tc_inv) {
+            constexpr int KT = TciDims<NF>::K;
+            TciArgs ta;
+            memset(&ta, 0, sizeof(ta));
+            ta.Y = (const float2*)Y;
+            ta.out = out + (size_t)v0 * p->vol_real;
+            int rct = tc_inv_table(p, NF, KT, &ta.tab);
+            if (rct != MVTB_OK) return rct;
+            ta.vols = dv; ta.vol_base = v0; ta.shared_desc = shared_desc;
+            ta.H = g.H; ta.NC = (int)g.NC; ta.W = g.W; ta.D = g.D;
+            ta.tiles_per_vol = (int)((g.NC + 127) / 128);
+            ta.n_vols = nv;
+            if (ta.tiles_per_vol >= p->num_sms) {         // big volumes: a few at a time, so that B's plane-wave columns last
+                ta.par_vols = nv < p->tci_par_vols ? nv : p->tci_par_vols;
+                ta.ctas_per_vol = p->num_sms / ta.par_vols;
+            } else {
+                ta.ctas_per_vol = ta.tiles_per_vol;
+                ta.par_vols = p->num_sms / ta.ctas_per_vol;
+                if (ta.par_vols > nv) ta.par_vols = nv;
+            }
+            ta.n_stages = tci_stages;
+            ta.vps = minmax_out ? vps : 1;
+            ta.minmax = minmax_out;
+            ta.status = p->tc_status;
+            ta.prof = nullptr;
+            static long long* dprof_i = nullptr;
+            if (getenv("MVTB_TC_PROF")) {                      // measurements: waits of CTA 0 of each launch, printed at the next call
+                const size_t np = 3 * 1024;
+                if (!dprof_i) { MVTB_CUDA(cudaMalloc((void**)&dprof_i, np * sizeof(long long))); }
+                else {
+                    std::vector<long long> h(np);
+                    MVTB_CUDA(cudaMemcpy(h.data(), dprof_i, np * sizeof(long long), cudaMemcpyDeviceToHost));
+                    for (int k = 0; k < 3; ++k) {
+                        const long long* q = h.data() + k * 1024;
+                        if (!q[0]) continue;
+                        fprintf(stderr, "k_bl_inv_tc launch %d CTA 0: total %lld cycles, %lld tiles; per tile: build[loads landed, stage free, arrived] issue[a_full, d_empty, committed] epi0[mma_done, drained] epi1[mma_done, drained]\n", k, q[0], q[6]);
+                        for (int t = 0; t < 40; ++t) {
+                            fprintf(stderr, "  tile %2d:", t);
+                            for (int e = 0; e < 10; ++e) fprintf(stderr, " %7lld%s", q[64 + 16 * t + e], (e == 2 || e == 5 || e == 7) ? " |" : "");
+                            fprintf(stderr, "\n");
+                        }
+                    }
+                }
+                MVTB_CUDA(cudaMemset(dprof_i, 0, np * sizeof(long long)));
+            }
+            const unsigned grid = (unsigned)(ta.par_vols * ta.ctas_per_vol);
+            if (tc_sel) {
+                {
+                    ProfScope prof(p, MVTB_K_BL_MM_TC, stream);
+                    auto kern = k_bl_inv_tc<NF, 0>;
+                    if (dprof_i && getenv("MVTB_TC_PROF")) ta.prof = dprof_i;
+                    MVTB_LAUNCH(kern, dim3(grid), dim3(kTciThreads), smem_tci, stream, ta);
+                }
+                if (!bits_launched) {
+                    int rcb = launch_bits(stream);
+                    if (rcb != MVTB_OK) return rcb;
+                } else {
+                    MVTB_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, p->ev_join, 0));
+                }
+                {
+                    ProfScope prof(p, MVTB_K_BL_INV_TC, stream);
+                    ta.bits = p->tc_bits;
+                    if (dprof_i && getenv("MVTB_TC_PROF")) ta.prof = dprof_i + 1024;
+                    auto kern = k_bl_inv_tc<NF, 2>;
+                    MVTB_LAUNCH(kern, dim3(grid), dim3(kTciThreads), smem_tci, stream, ta);
+                }
+            } else {
+                ProfScope prof(p, MVTB_K_BL_INV_TC, stream);
+                auto kern = k_bl_inv_tc<NF, 1>;
+                MVTB_LAUNCH(kern, dim3(grid), dim3(kTciThreads), smem_tci, stream, ta);
+            }
+        } else
+#endif
         if (fuse) {
             ProfScope prof(p, MVTB_K_BL_INV_SP, stream);
             ia.nsamp = nv / vps;
@@ -1029,7 +1213,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
     }
     MVTB_CUDA(cudaGetLastError());
-    if (sp) sp->done = fuse;
+    if (sp) sp->done = fuse || tc_sel;
     return MVTB_OK;
 }
 
@@ -1072,6 +1256,9 @@ static int bl_configure_nf(int optin) {
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 0>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 1>, optin)) != MVTB_OK) return rc;
     if (CPT == 2 && (rc = bl_big_smem(k_bl_inv_sp<NF, 2>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_tc<NF, 0>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_tc<NF, 1>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_tc<NF, 2>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
     MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MVTB_OK;
@@ -1093,6 +1280,7 @@ int configure_bl_kernels(const mvtb_plan* p) {
     if ((rc = bl_configure_nf<32>(optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_mid, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_fwd_tc, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_sp_bits, optin)) != MVTB_OK) return rc;
 #endif
     (void)p;
     return MVTB_OK;

@@ -185,10 +185,17 @@ struct mvtb_plan {
     int is_max_sample_mb;                 // samples larger than this take the separate select pass (their lines leave L2 first)
     unsigned* is_sync;                    // queue head + per-sample completion counters
     // tensor-core H-axis kernels (bandlimited_tc.cuh): operand tables per NF (built on first use), failure flag
-    int opt_tc;                           // 1: use them when the shape allows (MVTB_TC=1 or MVTB_PATH_BL_TC; off by default: see DESIGN 3.5)
+    int opt_tc;                           // 1: tensor-core forward H pass when the shape allows (MVTB_TC, default 1; MVTB_PATH_BL_TC / _CUDACORE)
+    int opt_tc_inv;                       // with opt_tc: the inverse pass too (MVTB_TC_INV, default 0: measured slower than the fused CUDA-core kernel; MVTB_PATH_BL_TC)
+    int opt_bits_overlap;                 // k_sp_bits on the plan's side stream, next to the W/D stage (MVTB_BITS_OVERLAP, default 1)
+    cudaStream_t side_stream;             // created on first use
+    cudaEvent_t ev_fork, ev_join;
+    int tci_par_vols;                     // inverse tensor-core pass: volumes in flight at a time (MVTB_TCI_PV, default 4)
     int tc_tma;                           // 1: the forward kernel stages x with TMA tensor-map copies (MVTB_TC_TMA=1); 0: coalesced LDG
     float* tc_tab_fwd[8];                 // by NF slot: [2][H * N] forward table (hi, lo)
     float* tc_tab_inv[8];                 // by NF slot: inverse table
+    unsigned* tc_bits;                    // (hit, coin) words of the select pass for one chunk of volumes (bandlimited_tci.cuh)
+    size_t tc_bits_bytes;
     int* tc_status;                       // device int: 0, or the code of the bounded wait that expired
     // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
     void* stage_h[MVTB_STAGE_SLOTS];

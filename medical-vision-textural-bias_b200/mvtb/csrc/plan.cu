@@ -136,7 +136,11 @@ extern "C" int mvtb_plan_create(mvtb_plan** out, int ndim_fft, const int* fft_sh
     p->opt_async = getenv("MVTB_NO_ASYNC") ? 0 : 1;
     p->opt_fusemid = getenv("MVTB_NO_FUSEMID") ? 0 : 1;
     p->opt_fusesp = getenv("MVTB_NO_FUSESP") ? 0 : 1;
-    p->opt_tc = getenv("MVTB_TC") ? atoi(getenv("MVTB_TC")) : 0;
+    p->opt_tc = getenv("MVTB_TC") ? atoi(getenv("MVTB_TC")) : 1;
+    p->opt_tc_inv = getenv("MVTB_TC_INV") ? atoi(getenv("MVTB_TC_INV")) : 0;
+    p->opt_bits_overlap = getenv("MVTB_BITS_OVERLAP") ? atoi(getenv("MVTB_BITS_OVERLAP")) : 1;
+    p->tci_par_vols = getenv("MVTB_TCI_PV") ? atoi(getenv("MVTB_TCI_PV")) : 4;
+    if (p->tci_par_vols < 1) p->tci_par_vols = 1;
     p->tc_tma = getenv("MVTB_TC_TMA") ? atoi(getenv("MVTB_TC_TMA")) : 0;
     p->is_chunk = getenv("MVTB_IS_CHUNK") ? atoi(getenv("MVTB_IS_CHUNK")) : 0;
     p->is_hs = getenv("MVTB_IS_HS") ? atoi(getenv("MVTB_IS_HS")) : 2;
@@ -363,6 +367,8 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
         if (p->tc_tab_inv[i]) cudaFree(p->tc_tab_inv[i]);
     }
     if (p->tc_status) cudaFree(p->tc_status);
+    if (p->tc_bits) cudaFree(p->tc_bits);
+    if (p->side_stream) { cudaStreamDestroy(p->side_stream); cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); }
     for (int s = 0; s < MVTB_STAGE_SLOTS; ++s) {
         if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
         if (p->stage_d[s]) cudaFree(p->stage_d[s]);
@@ -378,13 +384,14 @@ extern "C" unsigned long long mvtb_launch_count(void) { return g_launches.load()
 
 extern "C" const char* mvtb_kernel_name(int kind) {
     static const char* names[MVTB_K_KINDS] = {"k_rows_fwd", "k_axis<FWD>", "k_axis<MID>", "k_axis<INV>", "k_rows_inv",
-                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "k_rows_wrap", "k_bl_inv_sp", "k_bl_fwd_tc", "k_bl_inv_tc"};
+                                              "k_bl_fwd_h", "k_bl_fwd_w", "k_bl_mid", "k_bl_inv_w", "k_bl_inv_h", "k_spike_reduce", "k_spike_apply", "k_rows_wrap", "k_bl_inv_sp", "k_bl_fwd_tc", "k_bl_inv_tc", "k_bl_mm_tc", "k_sp_bits"};
     return (kind >= 0 && kind < MVTB_K_KINDS) ? names[kind] : "";
 }
 
 extern "C" int mvtb_plan_set_path(mvtb_plan* p, int path) {
     if (!p || path < MVTB_PATH_AUTO || path > MVTB_PATH_BL_TC) { set_error("plan_set_path: bad argument"); return MVTB_EINVAL; }
-    p->opt_tc = path == MVTB_PATH_BL_TC ? 1 : (path == MVTB_PATH_BL_CUDACORE ? 0 : (getenv("MVTB_TC") ? atoi(getenv("MVTB_TC")) : 0));
+    p->opt_tc = path == MVTB_PATH_BL_TC ? 1 : (path == MVTB_PATH_BL_CUDACORE ? 0 : (getenv("MVTB_TC") ? atoi(getenv("MVTB_TC")) : 1));
+    p->opt_tc_inv = path == MVTB_PATH_BL_TC ? 1 : (getenv("MVTB_TC_INV") ? atoi(getenv("MVTB_TC_INV")) : 0);
     p->opt_path = path == MVTB_PATH_GENERAL ? MVTB_PATH_GENERAL : MVTB_PATH_AUTO;
     p->opt_quad = path == MVTB_PATH_BL_PAIRS ? 0 : 1;
     p->opt_fusemid = (path == MVTB_PATH_BL_SPLIT || getenv("MVTB_NO_FUSEMID")) ? 0 : 1;

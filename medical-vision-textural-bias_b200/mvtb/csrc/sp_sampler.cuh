@@ -133,4 +133,41 @@ __device__ __forceinline__ void sp_walk_spans(float* __restrict__ xs, unsigned l
     }
 }
 
+// One span of `len` voxels, global id `gs`, walked by a warp in lock step: the same stream as sp_walk_spans (same
+// counters, words, coins and order), each hit handed to on_hit(position within the span, coin) instead of stored.
+template <typename F>
+__device__ __forceinline__ void sp_walk_span_cb(int len, unsigned long long gs, uint2 key, const unsigned* __restrict__ sT,
+                                                float inv_log2q, int lane, F on_hit) {
+    int base = 0;
+    unsigned iter = 0;
+    while (base < len) {
+        const uint4 r = Philox::run(make_uint4((unsigned)gs, (unsigned)(gs >> 32), iter * 32u + (unsigned)lane, MVTB_SP_TAG), key);
+        const unsigned words[3] = {r.x, r.y, r.z};
+        int pre[3], run = 0;
+        unsigned hitm = 0;
+        MVTB_UNROLL
+        for (int j = 0; j < 3; ++j) {
+            const int k = sp_invert(words[j], sT, inv_log2q);
+            const bool h = k < MVTB_SP_BLOCK;
+            hitm |= h ? (1u << j) : 0u;
+            run += h ? k + 1 : MVTB_SP_BLOCK;
+            pre[j] = run;
+        }
+        int incl = run;
+        MVTB_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int start = base + incl - run;
+        MVTB_UNROLL
+        for (int j = 0; j < 3; ++j) {
+            const int pos = start + pre[j] - 1;
+            if (((hitm >> j) & 1u) && pos < len) on_hit(pos, (r.w >> j) & 1u);
+        }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+        ++iter;
+    }
+}
+
 }  // namespace mvtb

@@ -130,6 +130,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tmap,
                  ::"r"(dst_smem), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+// 2-D tensor-map copy shared -> global (TMA store, UTMASTG), bulk-group completion; elements outside the tensor are not
+// written.  The shared-memory source must have been made visible with fence.proxy.async first.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(src_smem), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the latest N bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+// named barrier among `count` threads (a multiple of 32)
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
 // round to tf32 (10 explicit mantissa bits), nearest, ties away: what the tensor core then reads exactly
 __device__ __forceinline__ float to_tf32(float x) {
     uint32_t r;

@@ -74,3 +74,72 @@ def test_tc_chain127_with_spikes_and_minmax(cuda_device):
             ref = P.chain_127_exact_phase(xs[i], 12.5, idxs[i], 15.0, 0.5).numpy()
         assert rel_l2(y[i].cpu().numpy(), ref) <= TOL
         assert float(mm[i, 0]) == float(y[i].min()) and float(mm[i, 1]) == float(y[i].max())
+
+
+class _Path:
+    """plan of (shape3, n) pinned to a path, with the per-kernel profile on; .kinds after the block"""
+
+    def __init__(self, shape3, n, device, path):
+        from mvtb import _lib, functional as Fn
+        self.L, self.lib = _lib.lib(), _lib
+        self.plan = Fn.get_plan(shape3, n, device)
+        self.path = path
+        self.kinds = set()
+
+    def __enter__(self):
+        self.lib.check(self.L, self.L.mvtb_plan_set_path(self.plan, self.path))
+        self.lib.check(self.L, self.L.mvtb_plan_profile(self.plan, 1))
+        return self
+
+    def __exit__(self, *exc):
+        torch.cuda.synchronize()
+        ms, cn = (C.c_double * self.lib.K_KINDS)(), (C.c_int * self.lib.K_KINDS)()
+        self.lib.check(self.L, self.L.mvtb_plan_profile_read(self.plan, ms, cn))
+        self.kinds = {self.L.mvtb_kernel_name(k).decode() for k in range(self.lib.K_KINDS) if cn[k]}
+        st = self.L.mvtb_plan_tc_status(self.plan)
+        self.lib.check(self.L, self.L.mvtb_plan_profile(self.plan, 0))
+        self.lib.check(self.L, self.L.mvtb_plan_set_path(self.plan, 0))
+        assert st == 0, f"a tensor-core kernel gave up on an mbarrier wait (code {st})"
+        return False
+
+
+@pytest.mark.parametrize("shape,vps,p,r", [((6, 1, 64, 48, 40), 1, 0.05, 6.5), ((3, 2, 128, 128, 64), 2, 0.15, 12.5),
+                                           ((5, 1, 32, 36, 31), 1, 0.35, 6.5), ((2, 4, 64, 64, 30), 4, 0.08, 6.5),
+                                           ((3, 1, 48, 50, 30), 1, 0.05, 9.0), ((2, 1, 240, 240, 155), 1, 0.05, 12.5)])
+def test_tc_inverse_with_select_in_the_stores(cuda_device, shape, vps, p, r):
+    """Tensor-core path: compute-only (min, max) pass + (hit, coin) bits + store pass with the select applied ==
+    the same chain followed by mvtb_salt_pepper_sparse_f32, bit for bit (same spans, same Philox counters), in place
+    too; and the chain itself against the CUDA-core kernels."""
+    from mvtb import _lib, functional as Fn, host
+    from oracle import ref_port as P
+    x = torch.stack([P.synthetic_volume(i, shape[1:]) for i in range(shape[0])]).to(cuda_device)
+    thr = host.disk_threshold(r, shape[-3:])
+    descs = []
+    for b in range(shape[0]):
+        idx = (shape[2] // 2 + 9 + b % 3, shape[3] // 2 - 11, shape[4] // 2 + 8)       # outside the ball: plane waves
+        spikes = [(idx, host.exp_f32(9.0))]
+        if b % 2:
+            spikes.append(((shape[2] // 2 - 10, shape[3] // 2 + 9, shape[4] // 2 - 9), host.exp_f32(8.0)))
+        d = host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=spikes, wrap_alpha=0.25)
+        descs.extend([d] * vps)
+    n = shape[0] * vps
+    with _Path(shape[-3:], n, cuda_device, 5) as t1:
+        y3, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=vps)
+        y3 = y3.clone()
+    assert "k_bl_inv_tc" in t1.kinds and "k_bl_inv_h" not in t1.kinds and "k_bl_mm_tc" not in t1.kinds
+    for s in range(shape[0]):
+        assert float(mm[s, 0]) == float(y3[s].min()) and float(mm[s, 1]) == float(y3[s].max())
+    want = Fn.salt_pepper(y3, p, seed=31, offset=12345, n_samples=shape[0], mm=mm, sparse=True)
+    with _Path(shape[-3:], n, cuda_device, 5) as t2:
+        got, mm2 = Fn.kspace_chain_sp(x, 3, descs, p, seed=31, offset=12345, vols_per_sample=vps)
+        got = got.clone()
+        z = x.clone()
+        got2, _ = Fn.kspace_chain_sp(z, 3, descs, p, seed=31, offset=12345, vols_per_sample=vps, out=z)
+    assert {"k_bl_mm_tc", "k_sp_bits", "k_bl_inv_tc"} <= t2.kinds and "k_bl_inv_sp" not in t2.kinds
+    assert torch.equal(mm, mm2)
+    assert torch.equal(got, want) and not torch.equal(got, y3)
+    assert got2.data_ptr() == z.data_ptr() and torch.equal(z, want)
+    with _Path(shape[-3:], n, cuda_device, 4) as t3:
+        y_cc = Fn.kspace_chain(x, 3, descs, vols_per_sample=vps)
+    assert "k_bl_inv_tc" not in t3.kinds
+    assert rel_l2(y3.cpu().numpy(), y_cc.cpu().numpy()) <= 5e-6
