@@ -998,7 +998,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         if (tc_ring > kTcMaxRing) tc_ring = kTcMaxRing;
         if (tc_slots > 0) tc_ring -= tc_ring % tc_slots;          // a multiple of the converter groups (= slots): see the kernel
         const size_t smem_tc = tc_tab + (size_t)tc_ring * tc_bs * kTcRows * 128 * sizeof(float);
-        tc_fwd = p->opt_tc && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
+        // (with an intensity prologue the cp.async FFMA kernel applies the map as it reads: one pass instead of two)
+        tc_fwd = p->opt_tc && (pre_abt == nullptr || p->opt_tc_inv) && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
                  tc_ring >= 2 && tc_slots >= 2 && g.NC * (long long)g.H < 0x7fffffffLL;
 #endif
         {
