@@ -259,7 +259,7 @@ def gpu_step(cfg, x, idxs, out, step, group_offset=None):
     B, C = x.shape[0], x.shape[1]
     # the per-sample descriptors depend only on the configuration and the spike locations: built once, reused every step
     # (64 make_desc calls cost the host ~0.5 ms, a third of the step's GPU time)
-    key = (cfg["r"], cfg["spike"], cfg["alpha"], C, None if idxs is None else tuple(idxs))
+    key = (cfg["r"], cfg["spike"], cfg["alpha"], B, C, None if idxs is None else tuple(idxs))
     descs = _DESC_CACHE.get(key)
     if descs is None:
         thr = host.disk_threshold(cfg["r"], SHAPE)

@@ -844,7 +844,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 // and the separate pass is faster (4-channel BraTS samples of 143 MB: 9.4 k vs 8.9 k samples/s)
                 (size_t)vps * p->vol_real * sizeof(float) <= ((size_t)p->is_max_sample_mb << 20);
     // ---- tensor-core inverse pass (bandlimited_tci.cuh), with the select pass folded into its stores when asked for
-    bool tc_inv = false, tc_sel = false;
+    bool tc_inv = false, tc_sel = false, tc_fsel = false;
     size_t smem_tci = 0, smem_bits = 0;
     int tci_stages = 2;
     unsigned long long tc_bps = 0;
@@ -861,6 +861,8 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         tc_bps = ((unsigned long long)vps * p->vol_real + MVTB_SP_SPAN - 1) / MVTB_SP_SPAN;
         tc_sel = tc_inv && sp != nullptr && sp->p > 0.f && minmax_out != nullptr && vps >= 1 && vps <= kBlChunk &&
                  n_volumes % vps == 0 && smem_bits <= (size_t)200 * 1024 && tc_bps <= 0x7fffffffull;
+        // mode 3 (MVTB_TC_INV=2): the select pass inside the store kernel, sample by sample while its lines are in L2
+        tc_fsel = tc_sel && p->opt_tc_inv == 2 && (size_t)vps * p->vol_real * sizeof(float) <= ((size_t)p->is_max_sample_mb << 20);
         if (tc_inv) fuse = false;
     }
 #endif
@@ -918,6 +920,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     if (rc != MVTB_OK) return rc;
     const BlVol* dv = (const BlVol*)dvp;
     const cf* dtw = (const cf*)((const unsigned char*)dvp + vol_bytes);
+    if (tc_fsel && !p->is_sync) MVTB_CUDA(cudaMalloc((void**)&p->is_sync, sizeof(unsigned) * (size_t)(1 + kBlChunk)));
     if (fuse) {
         ia.pattern = (const unsigned*)((const unsigned char*)dvp + pat_off);
         ia.table = (const unsigned*)((const unsigned char*)dvp + tab_off);
@@ -1072,7 +1075,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
         }
 #ifndef MVTB_EMU
-        if (tc_sel && p->opt_bits_overlap) {
+        if (tc_sel && !tc_fsel && p->opt_bits_overlap) {
             if (!p->side_stream) {
                 MVTB_CUDA(cudaStreamCreateWithFlags(&p->side_stream, cudaStreamNonBlocking));
                 MVTB_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -1156,8 +1159,30 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 }
                 MVTB_CUDA(cudaMemset(dprof_i, 0, np * sizeof(long long)));
             }
+            if (tc_fsel && ta.tiles_per_vol >= p->num_sms) {          // one volume at a time: what is written must still be in L2 when it is selected
+                ta.par_vols = getenv("MVTB_TCI_PVF") ? atoi(getenv("MVTB_TCI_PVF")) : 1;
+                if (ta.par_vols > nv) ta.par_vols = nv;
+                ta.ctas_per_vol = p->num_sms / ta.par_vols;
+            }
+            ta.debug = getenv("MVTB_TCI_DEBUG") ? atoi(getenv("MVTB_TCI_DEBUG")) : 0;
             const unsigned grid = (unsigned)(ta.par_vols * ta.ctas_per_vol);
-            if (tc_sel) {
+            if (tc_fsel) {
+                ProfScope prof(p, MVTB_K_BL_INV_TC, stream);
+                const int nsamp = nv / vps;
+                MVTB_CUDA(cudaMemsetAsync(p->is_sync, 0, sizeof(unsigned) * (size_t)(1 + nsamp), (cudaStream_t)stream));
+                ta.sync = p->is_sync;
+                ta.sp_table = (const unsigned*)((const unsigned char*)dvp + tab_off);
+                const double l2q = log2(1.0 - (double)sp->p);
+                ta.inv_log2q = (l2q < 0.0 && l2q > -1e300) ? (float)(1.0 / l2q) : 0.f;
+                ta.seed = sp->seed;
+                ta.offset = sp->offset;
+                ta.n_per_sample = (unsigned long long)vps * p->vol_real;
+                ta.bps = (unsigned)tc_bps;
+                ta.s_base = v0 / vps;
+                if (dprof_i && getenv("MVTB_TC_PROF")) ta.prof = dprof_i + 2048;
+                auto kern = k_bl_inv_tc<NF, 3>;
+                MVTB_LAUNCH(kern, dim3(grid), dim3(kTciThreads), smem_tci, stream, ta);
+            } else if (tc_sel) {
                 {
                     ProfScope prof(p, MVTB_K_BL_MM_TC, stream);
                     auto kern = k_bl_inv_tc<NF, 0>;
@@ -1260,6 +1285,7 @@ static int bl_configure_nf(int optin) {
     if ((rc = bl_big_smem(k_bl_inv_tc<NF, 0>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_tc<NF, 1>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_inv_tc<NF, 2>, optin)) != MVTB_OK) return rc;
+    if ((rc = bl_big_smem(k_bl_inv_tc<NF, 3>, optin)) != MVTB_OK) return rc;
     if ((rc = bl_big_smem(k_bl_midw<NF>, optin)) != MVTB_OK) return rc;
     MVTB_CUDA(cudaFuncSetAttribute(k_bl_midw<NF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     return MVTB_OK;

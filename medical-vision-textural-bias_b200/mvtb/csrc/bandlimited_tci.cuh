@@ -34,10 +34,14 @@
 // GPU only (no emulator build); included by bandlimited.cu inside namespace mvtb.
 #pragma once
 #ifndef MVTB_EMU
+#ifndef MVTB_TCI_SEL_SPANS
+#define MVTB_TCI_SEL_SPANS 2
+#endif
 
 static const int kTciWarpBuild0 = 1, kTciWarpEpi0 = 9;
 static const int kTciEpiGroups = 4;            // (accumulator = tile parity, half of its row groups), 4 warps each
 static const int kTciThreads = 32 * (kTciWarpEpi0 + 4 * kTciEpiGroups);
+static const int kTciSelSpans = MVTB_TCI_SEL_SPANS;   // mode 3: spans a select warp walks in lock step
 static const int kTciPrefetch = 6;             // own tiles (every other tile of the CTA) between an L2 prefetch of Y and its use
 static const int kTciRowsPerWord = 16;         // rows of one column whose (hit, coin) bits share a 32-bit word = one tcgen05.ld.x16
 
@@ -58,6 +62,14 @@ struct TciArgs {
     int vps;                     // volumes per sample ((min, max) and the select values are per sample)
     float* minmax;               // 2 floats per sample of the call, or null
     const unsigned* bits;        // mode 2: [nvol][H / 16][NC] words, bits 2j, 2j+1 = (hit, coin) of row 16 rg + j
+    // mode 3: the select pass inside the kernel (warps 5-8), sample by sample as the counters fill
+    unsigned* sync;              // [n_vols / vps] finished (tile, epilogue warp) pairs per sample of the launch; zeroed before the launch
+    const unsigned* sp_table;    // sampler table T[k] (MVTB_SP_BLOCK entries)
+    float inv_log2q;
+    unsigned long long seed, offset, n_per_sample;
+    unsigned bps;                // spans per sample
+    int s_base;                  // index of the launch's first sample in the call
+    int debug;                   // MVTB_TCI_DEBUG, measurements: 1 = the select warps wait but do not walk, 2 = no fence before the counters (unsafe)
     int* status;
     long long* prof;             // null, or wait cycles of CTA 0 by warp and barrier kind (MVTB_TC_PROF)
 };
@@ -83,7 +95,9 @@ __device__ __forceinline__ unsigned long long tci_mad_wide(unsigned a, unsigned 
     return r;
 }
 
-// MODE 0: (min, max) only; 1: store (+ min/max when a.minmax); 2: store with the select applied (reads a.minmax, a.bits)
+// MODE 0: (min, max) only; 1: store (+ min/max when a.minmax); 2: store with the select applied (reads a.minmax, a.bits);
+// 3: store (L2 evict_last) + min/max + per-sample completion counters, and four warps that run the select pass of each
+//    sample as soon as it is complete, while its lines are still in L2 (one builder group then feeds the tensor core)
 template <int NF, int MODE>
 __global__ void __launch_bounds__(kTciThreads, 1)
 k_bl_inv_tc(TciArgs a) {
@@ -101,6 +115,9 @@ k_bl_inv_tc(TciArgs a) {
     constexpr int kAFloats = 128 * K;
 
     for (size_t i = tid; i < 2 * tab_floats / 4; i += blockDim.x) ((float4*)tci_smem)[i] = __ldg((const float4*)a.tab + i);
+    __shared__ unsigned s_spT[MODE == 3 ? MVTB_SP_BLOCK : 1];
+    if (MODE == 3)
+        for (int e = tid; e < MVTB_SP_BLOCK; e += blockDim.x) s_spT[e] = __ldg(a.sp_table + e);
     if (tid == 0) {
         s_abort = 0;
         for (int i = 0; i < 4; ++i) {
@@ -117,6 +134,7 @@ k_bl_inv_tc(TciArgs a) {
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
     volatile int* abortp = &s_abort;
+    constexpr int NBG = MODE == 3 ? 1 : 2;                 // builder groups
     // This CTA's tiles, in order: volumes pv, pv + P, ...; within a volume the tiles cv, cv + C, ...  The C CTAs of a
     // volume then write adjacent 512-byte row segments at about the same time -- measured with tools/wpat.cu, the
     // DRAM write stream of this pattern runs at 5.4 TB/s against 4.85 TB/s for a contiguous tile range per CTA (and
@@ -185,6 +203,31 @@ k_bl_inv_tc(TciArgs a) {
             __syncwarp();
             TCI_EV(tcount, 5);
         }
+    } else if (MODE == 3 && warp >= kTciWarpBuild0 + 4 && warp < kTciWarpEpi0) {
+        // ------------------------------------------------------------ select warps (mode 3): sample s once all its tiles are stored
+        const unsigned gsw = blockIdx.x * 4u + (unsigned)(warp - kTciWarpBuild0 - 4), nsw = gridDim.x * 4u;
+        const int n_samp = a.n_vols / a.vps;
+        const unsigned expected = (unsigned)a.vps * (unsigned)a.tiles_per_vol * 8u;      // 8 epilogue warps drain a tile
+        uint2 key;
+        key.x = (unsigned)a.seed;
+        key.y = (unsigned)(a.seed >> 32);
+        for (int sidx = 0; sidx < n_samp && !*abortp; ++sidx) {
+            bool ok = false;
+            for (int spin = 0; spin < (1 << 21); ++spin) {                               // bounded: ~1 s
+                if (ld_acquire_u32(a.sync + sidx) >= expected) { ok = true; break; }
+                if (*abortp) break;
+                __nanosleep(500);
+            }
+            if (!ok) { *abortp = 1; atomicCAS(a.status, 0, 16); break; }
+            const float* mm = a.minmax + 2 * (size_t)(a.s_base + sidx);
+            const float slo = 0.5f * __ldcg(mm), shi = 0.5f * __ldcg(mm + 1);
+            if (a.debug & 1) continue;                                                   // (measurement: no select work)
+            // kTciSelSpans spans at a time per warp: the tensor-core inverse leaves the SM's issue slots idle, so the walk is
+            // bound by its dependent chains (Philox, table search, prefix sum) and interleaved chains overlap them
+            for (unsigned span = gsw * kTciSelSpans; span < a.bps; span += nsw * kTciSelSpans)
+                sp_walk_spans<kTciSelSpans>(a.out + (size_t)sidx * a.n_per_sample, a.n_per_sample, span, a.bps,
+                                            a.offset + (unsigned long long)(a.s_base + sidx) * a.bps + span, key, s_spT, a.inv_log2q, slo, shi, lane);
+        }
     } else if (warp < kTciWarpEpi0) {
         // ------------------------------------------------------------ A builders: group = tile parity, thread = column of the tile
         // This path feeds the tensor core (two groups, one tile each per iteration), so per tile it does only what depends
@@ -196,7 +239,7 @@ k_bl_inv_tc(TciArgs a) {
         const int m = 32 * ((warp - kTciWarpBuild0) & 3) + lane;
         struct Loc { int k, vi; };
         auto loc_init = [&](int i) { Loc l; l.vi = nt_c ? i / nt_c : 0; l.k = i - l.vi * nt_c; return l; };
-        auto loc_adv = [&](Loc& l) { l.k += 2; while (l.k >= nt_c) { l.k -= nt_c; ++l.vi; } };
+        auto loc_adv = [&](Loc& l) { l.k += NBG; while (l.k >= nt_c) { l.k -= nt_c; ++l.vi; } };
         auto loc_vol = [&](const Loc& l) { return pv + l.vi * a.par_vols; };
         auto loc_col = [&](const Loc& l) { int c = (cv + l.k * a.ctas_per_vol) * 128 + m; return c < NC ? c : NC - 1; };   // past the end: computed, never stored
         float2 ynext[NF];
@@ -229,10 +272,10 @@ k_bl_inv_tc(TciArgs a) {
         loc_adv(ln);
         for (int i = 1; i < kTciPrefetch; ++i) {
             loc_adv(lp);
-            if ((int)grp + 2 * i < n_items) prefetch_y(lp);
+            if ((int)grp + NBG * i < n_items) prefetch_y(lp);
         }
         loc_adv(lp);
-        for (int tile = (int)grp; tile < n_items && !*abortp; tile += 2, loc_adv(lc), loc_adv(ln), loc_adv(lp)) {
+        for (int tile = (int)grp; tile < n_items && !*abortp; tile += NBG, loc_adv(lc), loc_adv(ln), loc_adv(lp)) {
             const unsigned tcount = (unsigned)tile, st = tcount % (unsigned)NST, ph = (tcount / (unsigned)NST) & 1u;
             const int vol = loc_vol(lc);
             const bool new_vol = vol != pvol;
@@ -312,8 +355,8 @@ k_bl_inv_tc(TciArgs a) {
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(tc::smem_u32(&bars.a_full[st]));
             if (warp == kTciWarpBuild0 + 4 * (int)grp) TCI_EV(tcount, 2);
-            if (tile + 2 < n_items) load_y(ln, ynext);                   // lands while the next tile waits for its stage
-            if (tile + 2 * kTciPrefetch < n_items) prefetch_y(lp);
+            if (tile + NBG < n_items) load_y(ln, ynext);                 // lands while the next tile waits for its stage
+            if (tile + NBG * kTciPrefetch < n_items) prefetch_y(lp);
         }
     } else {
         // ------------------------------------------------------------ epilogue: group = (tile parity, half of the row groups)
@@ -325,7 +368,8 @@ k_bl_inv_tc(TciArgs a) {
         const unsigned row_bytes = (unsigned)NC * 4u;
         float lo = __int_as_float(0x7f800000), hi = __int_as_float((int)0xff800000u);
         float sel_lo = 0.f, sel_hi = 0.f;
-        const bool want_mm = MODE == 0 || (MODE == 1 && a.minmax != nullptr);
+        const bool want_mm = MODE == 0 || MODE == 3 || (MODE == 1 && a.minmax != nullptr);
+        const unsigned long long pol = MODE == 3 ? l2_policy_evict_last() : 0ull;
         int cur_sample = -1;
         auto flush_mm = [&]() {
             MVTB_UNROLL
@@ -342,7 +386,7 @@ k_bl_inv_tc(TciArgs a) {
             locate(tile, vol, c0);
             const int sample = (a.vol_base + vol) / a.vps;
             if (sample != cur_sample) {
-                if (want_mm && cur_sample >= 0) flush_mm();
+                if (want_mm && MODE != 3 && cur_sample >= 0) flush_mm();
                 if (MODE == 2) {
                     sel_lo = 0.5f * __ldcg(a.minmax + 2 * (size_t)sample);
                     sel_hi = 0.5f * __ldcg(a.minmax + 2 * (size_t)sample + 1);
@@ -391,13 +435,21 @@ k_bl_inv_tc(TciArgs a) {
                             const float sv = (wb[r] & (2u << (2 * j))) ? sel_hi : sel_lo;
                             x = (wb[r] & (1u << (2 * j))) ? sv : x;
                         }
-                        __stcs((float*)tci_mad_wide(row_bytes, (unsigned)j, ob), x);
+                        float* o = (float*)tci_mad_wide(row_bytes, (unsigned)j, ob);
+                        if (MODE == 3) asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(o), "f"(x), "l"(pol) : "memory");
+                        else __stcs(o, x);
                     }
                 }
             }
             if (q == 0) TCI_EV(tcount, 7 + 2 * (int)half);
+            if (MODE == 3) {
+                flush_mm();                                              // the tile's (min, max) are in before it counts as stored
+                if (!(a.debug & 2)) __threadfence();                     // ... and so are this thread's rows, device-wide
+                __syncwarp();
+                if (lane == 0) atomicAdd(a.sync + vol / a.vps, 1u);
+            }
         }
-        if (want_mm && cur_sample >= 0) flush_mm();
+        if (want_mm && MODE != 3 && cur_sample >= 0) flush_mm();
     }
     tc::fence_before_sync();
     __syncthreads();

@@ -368,7 +368,9 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
     }
     if (p->tc_status) cudaFree(p->tc_status);
     if (p->tc_bits) cudaFree(p->tc_bits);
+#ifndef MVTB_EMU
     if (p->side_stream) { cudaStreamDestroy(p->side_stream); cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); }
+#endif
     for (int s = 0; s < MVTB_STAGE_SLOTS; ++s) {
         if (p->stage_h[s]) cudaFreeHost(p->stage_h[s]);
         if (p->stage_d[s]) cudaFree(p->stage_d[s]);

@@ -143,3 +143,42 @@ def test_tc_inverse_with_select_in_the_stores(cuda_device, shape, vps, p, r):
         y_cc = Fn.kspace_chain(x, 3, descs, vols_per_sample=vps)
     assert "k_bl_inv_tc" not in t3.kinds
     assert rel_l2(y3.cpu().numpy(), y_cc.cpu().numpy()) <= 5e-6
+
+
+@pytest.mark.parametrize("shape,vps,p,r", [((6, 1, 64, 48, 40), 1, 0.05, 6.5), ((3, 2, 128, 128, 64), 2, 0.15, 12.5),
+                                           ((3, 1, 48, 50, 30), 1, 0.05, 9.0), ((5, 1, 240, 240, 155), 1, 0.05, 12.5)])
+def test_tc_inverse_with_select_warps(cuda_device, monkeypatch, shape, vps, p, r):
+    """MVTB_TC_INV=2: one persistent kernel stores the tensor-core inverse pass and, on four more warps, runs the select
+    pass of every sample as soon as its tiles are counted complete == the two-call result, bit for bit."""
+    from mvtb import _lib, functional as Fn, host
+    from oracle import ref_port as P
+    x = torch.stack([P.synthetic_volume(i, shape[1:]) for i in range(shape[0])]).to(cuda_device)
+    thr = host.disk_threshold(r, shape[-3:])
+    descs = []
+    for b in range(shape[0]):
+        idx = (shape[2] // 2 + 9 + b % 3, shape[3] // 2 - 11, shape[4] // 2 + 8)
+        d = host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=[(idx, host.exp_f32(9.0))], wrap_alpha=0.25)
+        descs.extend([d] * vps)
+    n = shape[0] * vps
+    with _Path(shape[-3:], n, cuda_device, 5):
+        y3, mm = Fn.kspace_chain(x, 3, descs, want_minmax=True, vols_per_sample=vps)
+        y3 = y3.clone()
+    want = Fn.salt_pepper(y3, p, seed=77, offset=5, n_samples=shape[0], mm=mm, sparse=True)
+    monkeypatch.setenv("MVTB_TC_INV", "2")
+    Fn._destroy_plans()
+    try:
+        L = _lib.lib()
+        plan = Fn.get_plan(shape[-3:], n, cuda_device)
+        _lib.check(L, L.mvtb_plan_profile(plan, 1))
+        got, mm2 = Fn.kspace_chain_sp(x, 3, descs, p, seed=77, offset=5, vols_per_sample=vps)
+        torch.cuda.synchronize()
+        ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
+        _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
+        kinds = {L.mvtb_kernel_name(k).decode() for k in range(_lib.K_KINDS) if cn[k]}
+        assert L.mvtb_plan_tc_status(plan) == 0
+        got = got.clone()
+    finally:
+        Fn._destroy_plans()
+    assert "k_bl_inv_tc" in kinds and not ({"k_bl_mm_tc", "k_sp_bits", "k_bl_inv_sp", "k_bl_inv_h"} & kinds)
+    assert torch.equal(mm, mm2)
+    assert torch.equal(got, want) and not torch.equal(got, y3)
