@@ -6,6 +6,7 @@ Layout contract (same as the reference): contiguous float32, FFT over the last `
 every leading axis is a batch of independent volumes.
 """
 import atexit
+import math
 import ctypes as C
 import threading
 from collections import OrderedDict
@@ -41,10 +42,17 @@ def _cache() -> "OrderedDict":
     return c
 
 
+_cuda_ok = False
+
+
 def require_cuda() -> None:
+    global _cuda_ok
+    if _cuda_ok:                                        # a device does not go away; the query costs ~5 us per call
+        return
     if not torch.cuda.is_available():
         raise RuntimeError("mvtb: no CUDA device is available and there is no CPU fallback "
                            "(the transforms run only through libmvtb.so on a GPU)")
+    _cuda_ok = True
 
 
 def _stream(dev: torch.device) -> C.c_void_p:
@@ -94,7 +102,7 @@ def get_plan(fft_shape: Sequence[int], n_volumes: int, dev: torch.device):
     """The calling thread's plan for this shape on the current stream of `dev` (created on first use)."""
     fft_shape = tuple(int(s) for s in fft_shape)
     nh = fft_shape[-1] // 2 + 1
-    half_bytes = 8 * nh * int(np.prod(fft_shape[:-1]))
+    half_bytes = 8 * nh * math.prod(fft_shape[:-1])
     chunk = int(max(1, min(n_volumes, _WS_TARGET_BYTES // max(half_bytes, 1))))
     if chunk > 8:
         chunk = 1 << (chunk.bit_length() - 1)        # few distinct plans per shape
@@ -149,7 +157,7 @@ def kspace_chain(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDesc]
     if x.dim() < ndim_fft:
         raise ValueError(f"input of rank {x.dim()} has fewer than ndim_fft={ndim_fft} axes")
     fft_shape = tuple(x.shape[-ndim_fft:])
-    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    nvol = math.prod(x.shape[:-ndim_fft]) if x.dim() > ndim_fft else 1
     if len(descs) not in (1, nvol):
         raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
     y = torch.empty_like(x) if out is None else out
@@ -179,7 +187,7 @@ def kspace_chain_sp(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDe
     if x.dim() < ndim_fft:
         raise ValueError(f"input of rank {x.dim()} has fewer than ndim_fft={ndim_fft} axes")
     fft_shape = tuple(x.shape[-ndim_fft:])
-    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    nvol = math.prod(x.shape[:-ndim_fft]) if x.dim() > ndim_fft else 1
     if len(descs) not in (1, nvol):
         raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
     if nvol % vols_per_sample:
@@ -207,7 +215,7 @@ def kspace_chain_ex(x: torch.Tensor, ndim_fft: int, descs: Sequence[_lib.ChainDe
     if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous():
         raise ValueError("kspace_chain_ex expects a contiguous float32 CUDA tensor (use functional.to_device)")
     fft_shape = tuple(x.shape[-ndim_fft:])
-    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    nvol = math.prod(x.shape[:-ndim_fft]) if x.dim() > ndim_fft else 1
     if len(descs) not in (1, nvol):
         raise ValueError(f"need 1 or {nvol} descriptors, got {len(descs)}")
     if pre_abt is not None and (pre_abt.shape != (nvol, 3) or pre_abt.dtype != torch.float32 or pre_abt.device != x.device or not pre_abt.is_contiguous()):
@@ -296,7 +304,7 @@ def logabs_mean25(x: torch.Tensor, ndim_fft: int) -> torch.Tensor:
     """2.5 * mean(log(|fftn(x)| + 1e-10)) per volume, float32 on x.device (F:932-933, F:1127-1129)."""
     L = _lib.lib()
     fft_shape = tuple(x.shape[-ndim_fft:])
-    nvol = int(np.prod(x.shape[:-ndim_fft])) if x.dim() > ndim_fft else 1
+    nvol = math.prod(x.shape[:-ndim_fft]) if x.dim() > ndim_fft else 1
     plan = get_plan(fft_shape, nvol, x.device)
     sums = torch.empty(nvol, dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):

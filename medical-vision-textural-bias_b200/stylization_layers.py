@@ -62,12 +62,28 @@ class GibbsNoiseLayer(nn.Module, Fourier):
             alpha = min(max(alpha, 0.), 1.)
             self.alpha = torch.tensor([alpha], requires_grad=True, device=self.device)
 
+    def _alpha_on_host(self) -> float:
+        """alpha as a Python float.  The mask threshold is computed on the host (S:71 reads alpha there too), which for a CUDA
+        tensor costs a device-to-host copy and a stream synchronisation per forward; the value is read again only when
+        the attribute was reassigned (what the 350_stylized_layers scripts do) or written in place (version counter; a write
+        through `.data` bypasses that counter and is not seen), so that a loop that leaves alpha alone between
+        finite-difference updates pays for it once per update."""
+        a = self.alpha
+        if not isinstance(a, torch.Tensor):
+            return float(a)
+        cached = self.__dict__.get("_alpha_cache")
+        # the cache keeps the tensor itself (not its id(), which Python reuses once a tensor is freed)
+        if cached is None or cached[0] is not a or cached[1] != a._version:
+            cached = (a, a._version, float(a.detach().reshape(-1)[0]))
+            self.__dict__["_alpha_cache"] = cached
+        return cached[2]
+
     def forward(self, img: torch.Tensor) -> torch.Tensor:
         n_dims = len(img.shape[1:])
         if n_dims < 2 or n_dims > 4:
             raise ValueError(f"GibbsNoiseLayer supports inputs of rank 3 to 5, got rank {img.dim()}")
         x, src = Fn.to_device(img)
-        alpha = float(self.alpha.detach().reshape(-1)[0]) if isinstance(self.alpha, torch.Tensor) else float(self.alpha)
+        alpha = self._alpha_on_host()
         thresh = host.layer_threshold(np.float32(alpha), img.shape[1:])
         if x.requires_grad:
             y = _MaskedSpectrum.apply(x, n_dims, thresh)

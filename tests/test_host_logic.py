@@ -283,3 +283,23 @@ def test_bench_reference_arm_json_contract():
     assert line["e2e"] == {"value": line["value"], "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["value_1_thread"] > 0 and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
+
+
+def test_gibbs_layer_reads_alpha_once_per_update():
+    """GibbsNoiseLayer keeps alpha's host value until the attribute is reassigned or written in place (S:71 reads it
+    on the host every forward; on a CUDA tensor that is a synchronising copy)."""
+    import torch
+    import stylization_layers as S
+    layer = S.GibbsNoiseLayer(0.7)
+    layer.alpha = torch.tensor([0.7])
+    assert layer._alpha_on_host() == pytest.approx(0.7)
+    first = layer._alpha_cache
+    assert layer._alpha_on_host() == pytest.approx(0.7) and layer._alpha_cache is first      # no second read
+    old = layer.alpha.clone()
+    layer.alpha = old + 0.1                                                                   # the scripts' update (GD.py:261)
+    assert layer._alpha_on_host() == pytest.approx(0.8) and layer._alpha_cache is not first
+    with torch.no_grad():
+        layer.alpha -= 0.3                                                                    # in place: version counter
+    assert layer._alpha_on_host() == pytest.approx(0.5)
+    layer.alpha = 0.25                                                                        # a plain float is accepted too
+    assert layer._alpha_on_host() == 0.25
