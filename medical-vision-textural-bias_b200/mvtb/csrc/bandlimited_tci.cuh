@@ -179,6 +179,7 @@ k_bl_inv_tc(TciArgs a) {
                 uint32_t acc = 0;
                 MVTB_UNROLL
                 for (int term = 0; term < 3; ++term) {                  // lo*hi, hi*lo, then hi*hi
+                    if (term == 1 && (a.debug & 4)) continue;           // (measurement: two terms only)
                     const uint32_t aa = term == 0 ? al : ah, bb = term == 1 ? bl : bh;
                     MVTB_UNROLL
                     for (int j = 0; j < KS; ++j) {
