@@ -7,6 +7,7 @@ module, so `-m "not gpu"` tests cover it.
 
 F = source_code/filters_and_operators.py, S = source_code/stylization_layers.py of the reference.
 """
+import ctypes
 from functools import lru_cache
 from math import floor
 from typing import Iterable, Optional, Sequence, Tuple
@@ -135,6 +136,9 @@ def make_desc(*, mask_kind: int = _lib.MASK_NONE, mask_ndim: int = 0, mask_thres
 
 
 def desc_array(descs: Sequence[_lib.ChainDesc]):
+    """The contiguous ChainDesc array the C ABI takes; an array made earlier is passed through as it is."""
+    if isinstance(descs, ctypes.Array):
+        return descs
     arr = (_lib.ChainDesc * len(descs))()
     for i, d in enumerate(descs):
         arr[i] = d

@@ -18,9 +18,10 @@ x = torch.randn(B, 1, 128, 128, 64, device=dev)
 idxs = [(64 + (b % 5), 64 - (b % 7), 32 + (b % 3)) for b in range(B)]
 layer = S.GibbsNoiseLayer(float(sys.argv[2]) if len(sys.argv) > 2 else 0.7)
 plan = Fn.get_plan((128, 128, 64), B, dev)
+plan_layer = Fn.get_plan((1, 128, 128, 64), B, dev)           # the layer transforms over (C, H, W, D)
 
 
-def timed(name, fn, n=10):
+def timed(name, fn, n=10, plan=plan):
     with torch.no_grad():
         for _ in range(3):
             fn()
@@ -41,4 +42,4 @@ def timed(name, fn, n=10):
 
 y = Fn.chain127(x, r=12.5, spike_idx=idxs, intensity=15.0, alpha=0.5, p=0.05, seed=7, sparse=True)
 timed("chain127", lambda: Fn.chain127(x, r=12.5, spike_idx=idxs, intensity=15.0, alpha=0.5, p=0.05, seed=7, sparse=True))
-timed("layer", lambda: layer(y))
+timed("layer", lambda: layer(y), plan=plan_layer)
