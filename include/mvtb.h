@@ -32,6 +32,8 @@ extern "C" {
 #define MVTB_EUNSUPPORTED (-2)  /* shape / option outside what the kernels implement */
 #define MVTB_ENOMEM (-3)
 #define MVTB_ENODEVICE (-4)     /* no usable CUDA device: there is no CPU fallback */
+#define MVTB_ETIMEOUT (-5)      /* a tensor-core kernel of an EARLIER call on this plan gave up on an mbarrier wait (that call's output is
+                                   invalid); the plan has switched to the CUDA-core kernels.  Never seen outside a protocol bug. */
 
 #define MVTB_MAX_FFT_DIMS 4
 #define MVTB_MAX_SPIKES 8

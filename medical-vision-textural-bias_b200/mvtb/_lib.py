@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmvtb.so")
 
-MVTB_OK, MVTB_EINVAL, MVTB_EUNSUPPORTED, MVTB_ENOMEM, MVTB_ENODEVICE = 0, -1, -2, -3, -4
+MVTB_OK, MVTB_EINVAL, MVTB_EUNSUPPORTED, MVTB_ENOMEM, MVTB_ENODEVICE, MVTB_ETIMEOUT = 0, -1, -2, -3, -4, -5
 MASK_NONE, MASK_DISK, MASK_CENTRED, MASK_UNIFORM = 0, 1, 2, 3
 MAX_FFT_DIMS, MAX_SPIKES = 4, 8
 

@@ -944,6 +944,21 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
     const size_t smem_hi = smem_h + sizeof(cf) * MVTB_BL_MAX_PW * (g.H / 2 + 1);
     const size_t smem_mid = sizeof(cf) * ((size_t)2 * K * g.D + (size_t)K * K);
 
+#ifndef MVTB_EMU
+    // Fail loudly, if late: every tensor-core wait is bounded, and a kernel that gives up leaves a code in tc_status.
+    // The flag travels to a pinned host word at the end of each call (no synchronisation), so a later call sees it.
+    if (p->tc_status_h && *(volatile int*)p->tc_status_h != 0) {
+        const int code = *(volatile int*)p->tc_status_h;
+        p->opt_tc = 0;
+        p->opt_tc_inv = 0;
+        *(volatile int*)p->tc_status_h = 0;
+        cudaMemsetAsync(p->tc_status, 0, sizeof(int), (cudaStream_t)stream);
+        set_error("band-limited path: a tensor-core kernel of an earlier call on this plan gave up on an mbarrier wait (code %d); "
+                  "that call's output is invalid; the plan now uses the CUDA-core kernels", code);
+        return MVTB_ETIMEOUT;
+    }
+#endif
+    bool tc_used = false;
     for (int v0 = 0; v0 < n_volumes; v0 += chunk) {
         const int nv = n_volumes - v0 < chunk ? n_volumes - v0 : chunk;
         cf* Y = p->bl_ws;
@@ -1048,6 +1063,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 }
                 const unsigned grid = (unsigned)(ta.n_tiles < p->num_sms ? ta.n_tiles : p->num_sms);
                 MVTB_LAUNCH(k_bl_fwd_tc, dim3(grid), dim3(kTcFwdThreads), smem_tc, stream, tmap, ta);
+                tc_used = true;
             } else
 #endif
             {
@@ -1166,6 +1182,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
             ta.debug = getenv("MVTB_TCI_DEBUG") ? atoi(getenv("MVTB_TCI_DEBUG")) : 0;
             const unsigned grid = (unsigned)(ta.par_vols * ta.ctas_per_vol);
+            tc_used = true;
             if (tc_fsel) {
                 ProfScope prof(p, MVTB_K_BL_INV_TC, stream);
                 const int nsamp = nv / vps;
@@ -1238,6 +1255,15 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
             }
         }
     }
+#ifndef MVTB_EMU
+    if (tc_used && p->tc_status) {
+        if (!p->tc_status_h) {
+            MVTB_CUDA(cudaMallocHost((void**)&p->tc_status_h, sizeof(int)));
+            *p->tc_status_h = 0;
+        }
+        MVTB_CUDA(cudaMemcpyAsync(p->tc_status_h, p->tc_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    }
+#endif
     MVTB_CUDA(cudaGetLastError());
     if (sp) sp->done = fuse || tc_sel;
     return MVTB_OK;

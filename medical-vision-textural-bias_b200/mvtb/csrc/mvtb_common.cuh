@@ -197,6 +197,7 @@ struct mvtb_plan {
     unsigned* tc_bits;                    // (hit, coin) words of the select pass for one chunk of volumes (bandlimited_tci.cuh)
     size_t tc_bits_bytes;
     int* tc_status;                       // device int: 0, or the code of the bounded wait that expired
+    int* tc_status_h;                     // pinned host copy, refreshed (asynchronously) at the end of every call that ran a tensor-core kernel
     // ring of pinned-host / device staging slots for per-call parameter arrays (plan_stage_upload)
     void* stage_h[MVTB_STAGE_SLOTS];
     void* stage_d[MVTB_STAGE_SLOTS];

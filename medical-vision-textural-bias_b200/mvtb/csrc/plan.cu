@@ -367,6 +367,7 @@ extern "C" int mvtb_plan_destroy(mvtb_plan* p) {
         if (p->tc_tab_inv[i]) cudaFree(p->tc_tab_inv[i]);
     }
     if (p->tc_status) cudaFree(p->tc_status);
+    if (p->tc_status_h) cudaFreeHost(p->tc_status_h);
     if (p->tc_bits) cudaFree(p->tc_bits);
 #ifndef MVTB_EMU
     if (p->side_stream) { cudaStreamDestroy(p->side_stream); cudaEventDestroy(p->ev_fork); cudaEventDestroy(p->ev_join); }
