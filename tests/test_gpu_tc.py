@@ -182,3 +182,22 @@ def test_tc_inverse_with_select_warps(cuda_device, monkeypatch, shape, vps, p, r
     assert "k_bl_inv_tc" in kinds and not ({"k_bl_mm_tc", "k_sp_bits", "k_bl_inv_sp", "k_bl_inv_h"} & kinds)
     assert torch.equal(mm, mm2)
     assert torch.equal(got, want) and not torch.equal(got, y3)
+
+
+@pytest.mark.parametrize("shape,r,expect_tc", [((70, 1, 16, 20, 12), 3.0, True),       # more volumes than a chunk, the smallest H
+                                               ((3, 1, 32, 15, 7), 3.0, False),        # W*D % 4 != 0: no TMA rows, FFMA kernel
+                                               ((3, 1, 40, 36, 32), 6.5, False)])      # H % 16 != 0
+def test_default_path_picks_the_forward_kernel_by_shape(cuda_device, shape, r, expect_tc):
+    """The automatic path runs the tensor-core forward kernel exactly when its layout conditions hold, and either way
+    matches the oracle."""
+    from mvtb import _lib, functional as Fn, host
+    from oracle import ref_port as P
+    xs = [P.synthetic_volume(300 + i, shape[1:]) for i in range(min(shape[0], 2))]
+    x = torch.stack([xs[i % len(xs)] for i in range(shape[0])]).to(cuda_device)
+    d = [host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=host.disk_threshold(r, shape[-3:]))]
+    with _Path(shape[-3:], shape[0], cuda_device, 0) as t:
+        y = Fn.kspace_chain(x, 3, d).clone()
+    assert ("k_bl_fwd_tc" in t.kinds) == expect_tc and ("k_bl_fwd_h" in t.kinds) == (not expect_tc)
+    ref = P.fourier_disk_mask(xs[0], r, False).numpy()
+    assert rel_l2(y[0].cpu().numpy(), ref) <= TOL
+    assert torch.equal(y[len(xs)], y[0])                     # same input volume, another chunk slot / tile range: same bits
