@@ -9,7 +9,8 @@
  *   - every function returns 0 (MVTB_OK) on success, a negative MVTB_E* code for argument
  *     errors, or a positive cudaError_t; nothing throws, nothing calls exit();
  *   - all work is enqueued asynchronously on the caller's stream (`stream` is a cudaStream_t
- *     passed as void*); only plan_create/plan_destroy may synchronise;
+ *     passed as void*); plan_create/plan_destroy synchronise; a transform call blocks the host only when a workspace has to grow
+ *     (first call of a plan on a larger batch) or a pinned staging slot is still in flight;
  *   - the caller owns every in/out/u/minmax device buffer; the plan owns its tables and
  *     workspace; a plan is used from one stream at a time;
  *   - tensors are contiguous row-major fp32; a "volume" is one block of the last `ndim_fft`
