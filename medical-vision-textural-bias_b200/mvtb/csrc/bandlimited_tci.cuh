@@ -265,7 +265,7 @@ k_bl_inv_tc(TciArgs a) {
             int r = pr - q * N;
             if (r < 0) r += N;
             if (r >= N) r -= N;
-            sincospif(2.0f * (float)r * invN, &s_, &c_);
+            sincospif(2.0f * (float)r / (float)N, &s_, &c_);             // the correctly rounded quotient, as bl_unit32 (r * (1/N) is an ulp worse)
         };
         const float invW = 1.0f / (float)a.W, invD = 1.0f / (float)a.D, invH = 1.0f / (float)H;
         Loc lc = loc_init((int)grp), ln = lc, lp = lc;
