@@ -190,6 +190,13 @@ int mvtb_dice_grad_f32(const float* x, const float* target, size_t n_per_vol, in
  * frequency-consistency loss of 50_reconstruction/reconGan/reconGan_freq.py:134-140 needs no transform. */
 int mvtb_sqdiff_sum_f32(const float* a, const float* b, size_t n, double* sum_out, void* scratch, void* stream);
 
+/* RandSpatialCropd / CenterSpatialCropd followed by RandFlipd (MONAI 0.5; 127_...FLAIR.py:130-133, :153) as one gather on a
+ * (C, H, W, D) sample:  out[c][i][j][k] = in[c][o0 + (f0 ? s0-1-i : i)][o1 + (f1 ? s1-1-j : j)][o2 + (f2 ? s2-1-k : k)],
+ * in_shape = (H, W, D), out_shape = (s0, s1, s2), offset = (o0, o1, o2) with o + s <= N on every axis, flip_axes_mask bit a =
+ * spatial axis a reversed (np.flip after the crop).  The host draws offsets and flips in MONAI's order. in != out. */
+int mvtb_crop_flip_f32(const float* in, float* out, int n_channels, const int32_t* in_shape, const int32_t* out_shape,
+                       const int32_t* offset, int flip_axes_mask, void* stream);
+
 /* WrapArtifact (F:503-515) on (C,H,W,D) when H, W and D are all even: the image-domain fold
  * out = prod_axes (c0 + s c1 Roll_{N/2}) x, c0=(1+alpha)/2, c1=(1-alpha)/2, s=(-1)^(N/2)
  * (SURVEY A.3).  Returns MVTB_EUNSUPPORTED for an odd axis (use the chain). in != out. */

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "medical-vision-textural-bias_b200", "mvtb", "csrc")
 OUT = os.path.join(HERE, "_build", "libmvtb_emu.so")
-SOURCES = ["plan.cu", "kspace_chain.cu", "voxel_ops.cu", "bandlimited.cu", "spike_fast.cu", "intensity.cu", "dice.cu"]
+SOURCES = ["plan.cu", "kspace_chain.cu", "voxel_ops.cu", "bandlimited.cu", "spike_fast.cu", "intensity.cu", "dice.cu", "spatial.cu"]
 
 
 def build(force=False):
