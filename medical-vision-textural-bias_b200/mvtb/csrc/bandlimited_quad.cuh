@@ -602,6 +602,12 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
 // Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
 // CTAs per SM: 4 up to NF = 16 (96 registers), 3 at NF = 20, 2 beyond (the 4 NF accumulator registers dominate)
 #define MVTB_MIDW_MINB(NF) ((NF) <= 16 ? 4 : ((NF) <= 20 ? 3 : 2))
+#ifndef MVTB_EMU
+__device__ long long g_midw_prof[8];     // MVTB_MID_PROF: clock64 of CTA 0 at the phase boundaries of the last launch
+#define MVTB_MIDW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_midw_prof[i] = clock64(); } while (0)
+#else
+#define MVTB_MIDW_STAMP(i) do { } while (0)
+#endif
 template <int NF>
 __global__ void __launch_bounds__(160, MVTB_MIDW_MINB(NF))
 k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
@@ -620,7 +626,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     const int vol = blockIdx.x / NF, fh = blockIdx.x - vol * NF;
     bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);
     for (int e = tid; e < D; e += nthr) st[e] = __ldg(g.twD + e);
-    __syncthreads();
+    __syncthreads(); MVTB_MIDW_STAMP(0);
     cf* yplane = Y + ((size_t)vol * NF + fh) * (size_t)W * D;
     const int npair = (W - 1) / 2;
 
@@ -668,7 +674,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); MVTB_MIDW_STAMP(1);
 
     // ---- D axis forward, pair-folded like the other axes: with e = G[d] + G[D-d], o = G[d] - G[D-d] (in place),
     //   B(+-fd) = G[0] (+ G[D/2] (-1)^fd) + P -+ iQ,   P = sum_d e cos(2 pi fd d / D),  Q = sum_d o sin(2 pi fd d / D)
@@ -716,7 +722,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             }
         }
     }
-    __syncthreads();
+    __syncthreads(); MVTB_MIDW_STAMP(2);
     // E = B(+fd) + B(-fd), O = B(+fd) - B(-fd) packed as float4 over the now free G tile: the way back along D is
     //   G'[j][d] = B(0) + sum_fd ( E cos(2 pi fd d / D) + i O sin(2 pi fd d / D) )
     float4* seo = (float4*)sg;                            // [K][F + 1]; entry 0 of a row holds (B(0), 0)
@@ -727,7 +733,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     }
     __syncthreads();
     bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);      // over the bins, which are no longer needed
-    __syncthreads();
+    __syncthreads(); MVTB_MIDW_STAMP(3);
 
     // ---- back along D (into registers) and along W (streamed out in place)
     for (int d = tid; d < D; d += nthr) {
@@ -797,4 +803,5 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             yv[(size_t)(W - w) * D] = cmk(Px + Qy, Py - Qx);
         }
     }
+    MVTB_MIDW_STAMP(4);
 }
