@@ -1108,18 +1108,18 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
 #endif
         const size_t smem_mw = bl_midw_smem<NF>(g, K);
+#ifndef MVTB_EMU
+        if (getenv("MVTB_MID_PROF")) {                    // phase boundaries of CTA 0 of the previous launch
+            long long h[8];
+            if (cudaMemcpyFromSymbol(h, g_midw_prof, sizeof(h)) == cudaSuccess && h[4] > h[0])
+                fprintf(stderr, "k_bl_midw CTA 0: W forward %lld, D axis + pointwise %lld, repack + table %lld, D/W back %lld cycles\n",
+                        h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
+        }
+#endif
         if (!split_mid) {                                                   // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);
             auto kern = k_bl_midw<NF>;
-#ifndef MVTB_EMU
-            if (getenv("MVTB_MID_PROF")) {                    // phase boundaries of CTA 0 of the previous launch
-                long long h[8];
-                if (cudaMemcpyFromSymbol(h, g_midw_prof, sizeof(h)) == cudaSuccess && h[4] > h[0])
-                    fprintf(stderr, "k_bl_midw CTA 0: W forward %lld, D axis + pointwise %lld, repack + table %lld, D/W back %lld cycles\n",
-                            h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
-            }
-#endif
             MVTB_LAUNCH(kern, dim3((unsigned)(nv * NF)), dim3(160), smem_mw, stream, Y, g, dv, v0, shared_desc);
         } else {
             {

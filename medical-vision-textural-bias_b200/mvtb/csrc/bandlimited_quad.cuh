@@ -602,6 +602,10 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
 // Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
 // CTAs per SM: 4 up to NF = 16 (96 registers), 3 at NF = 20, 2 beyond (the 4 NF accumulator registers dominate)
 #define MVTB_MIDW_MINB(NF) ((NF) <= 16 ? 4 : ((NF) <= 20 ? 3 : 2))
+#ifndef MVTB_MID_PREFETCH
+#define MVTB_MID_PREFETCH 0      // 0 = off: measured 3.26 (two batches ahead) / 3.4 (one) against 3.02 us per volume without
+#endif
+static const int kMidPrefetch = MVTB_MID_PREFETCH;
 #ifndef MVTB_EMU
 __device__ long long g_midw_prof[8];     // MVTB_MID_PROF: clock64 of CTA 0 at the phase boundaries of the last launch
 #define MVTB_MIDW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_midw_prof[i] = clock64(); } while (0)
@@ -646,8 +650,19 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
         int w = 1;
         for (; w + U - 1 <= npair; w += U) {
             cf a[U], b[U];
-            // (L2 prefetches of the rows one or two batches ahead make CTA 0's W-axis pass 2.6x faster by MVTB_MID_PROF's stamps
-            // and the kernel as a whole 20-30 % slower -- 3.63 / 3.99 against 3.02 us per volume: not used)
+#ifndef MVTB_EMU
+            // Y was written by the forward kernel a whole chunk (247 MB) ago: these loads come from DRAM, and with 20 warps per
+            // SM their latency is what the W-axis pass mostly waits for (MVTB_MID_PROF: 121 k of a CTA's 242 k cycles).  One
+            // thread per 128-byte line can ask L2 for the rows kMidPrefetch batches ahead -- CTA 0's pass then takes 47 k cycles,
+            // but the kernel as a whole gets slower (see MVTB_MID_PREFETCH), so this is compiled out by default.
+            if (kMidPrefetch > 0 && (d & 15) == 0 && w + (kMidPrefetch + 1) * U - 1 <= npair) {
+                MVTB_UNROLL
+                for (int u = 0; u < U; ++u) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(yv + (size_t)(w + kMidPrefetch * U + u) * D));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(yv + (size_t)(W - w - kMidPrefetch * U - u) * D));
+                }
+            }
+#endif
             MVTB_UNROLL
             for (int u = 0; u < U; ++u) { a[u] = yv[(size_t)(w + u) * D]; b[u] = yv[(size_t)(W - w - u) * D]; }
             MVTB_UNROLL
