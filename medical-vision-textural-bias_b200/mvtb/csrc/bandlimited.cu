@@ -1108,14 +1108,10 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         }
 #endif
         const size_t smem_mw = bl_midw_smem<NF>(g, K);
-#ifndef MVTB_EMU
-        if (getenv("MVTB_MID_PROF")) {                    // phase boundaries of CTA 0 of the previous launch
-            long long h[8];
-            if (cudaMemcpyFromSymbol(h, g_midw_prof, sizeof(h)) == cudaSuccess && h[4] > h[0])
-                fprintf(stderr, "k_bl_midw CTA 0: W forward %lld, D axis + pointwise %lld, repack + table %lld, D/W back %lld cycles\n",
-                        h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
-        }
-#endif
+        // (k_bl_midw measured with clock64 stamps at its phase boundaries, since removed -- the volatile clock reads cost 32 bytes
+        // of spills and a third of the kernel's speed: a CTA spends 50 % in the W-axis forward pass, 13 % in the D axis + pointwise
+        // stage, 35 % on the way back.  L2 prefetches of the rows ahead, by every 16th computing thread or by the five threads
+        // without a column, made CTA 0's forward pass 2.6x faster and the kernel 8-50 % slower)
         if (!split_mid) {                                                   // at least 2 CTAs per SM
             // W axis forward + D axis + pointwise + W axis back in one kernel per (volume, f_h) plane
             ProfScope prof(p, MVTB_K_BL_MID, stream);

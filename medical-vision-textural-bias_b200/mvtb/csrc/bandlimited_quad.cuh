@@ -602,16 +602,6 @@ k_bl_fwd_h4a(const float* __restrict__ x, cf* __restrict__ Y, BlGeom g, int n_cb
 // Y in place.  The G workspace and two launches disappear; the plane is read once and written once.
 // CTAs per SM: 4 up to NF = 16 (96 registers), 3 at NF = 20, 2 beyond (the 4 NF accumulator registers dominate)
 #define MVTB_MIDW_MINB(NF) ((NF) <= 16 ? 4 : ((NF) <= 20 ? 3 : 2))
-#ifndef MVTB_MID_PREFETCH
-#define MVTB_MID_PREFETCH 0      // 0 = off: measured 3.26 (two batches ahead) / 3.4 (one) against 3.02 us per volume without
-#endif
-static const int kMidPrefetch = MVTB_MID_PREFETCH;
-#ifndef MVTB_EMU
-__device__ long long g_midw_prof[8];     // MVTB_MID_PROF: clock64 of CTA 0 at the phase boundaries of the last launch
-#define MVTB_MIDW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_midw_prof[i] = clock64(); } while (0)
-#else
-#define MVTB_MIDW_STAMP(i) do { } while (0)
-#endif
 template <int NF>
 __global__ void __launch_bounds__(160, MVTB_MIDW_MINB(NF))
 k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_base, int shared_desc) {
@@ -630,7 +620,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     const int vol = blockIdx.x / NF, fh = blockIdx.x - vol * NF;
     bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);
     for (int e = tid; e < D; e += nthr) st[e] = __ldg(g.twD + e);
-    __syncthreads(); MVTB_MIDW_STAMP(0);
+    __syncthreads();
     cf* yplane = Y + ((size_t)vol * NF + fh) * (size_t)W * D;
     const int npair = (W - 1) / 2;
 
@@ -650,19 +640,6 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
         int w = 1;
         for (; w + U - 1 <= npair; w += U) {
             cf a[U], b[U];
-#ifndef MVTB_EMU
-            // Y was written by the forward kernel a whole chunk (247 MB) ago: these loads come from DRAM, and with 20 warps per
-            // SM their latency is what the W-axis pass mostly waits for (MVTB_MID_PROF: 121 k of a CTA's 242 k cycles).  One
-            // thread per 128-byte line can ask L2 for the rows kMidPrefetch batches ahead -- CTA 0's pass then takes 47 k cycles,
-            // but the kernel as a whole gets slower (see MVTB_MID_PREFETCH), so this is compiled out by default.
-            if (kMidPrefetch > 0 && (d & 15) == 0 && w + (kMidPrefetch + 1) * U - 1 <= npair) {
-                MVTB_UNROLL
-                for (int u = 0; u < U; ++u) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(yv + (size_t)(w + kMidPrefetch * U + u) * D));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(yv + (size_t)(W - w - kMidPrefetch * U - u) * D));
-                }
-            }
-#endif
             MVTB_UNROLL
             for (int u = 0; u < U; ++u) { a[u] = yv[(size_t)(w + u) * D]; b[u] = yv[(size_t)(W - w - u) * D]; }
             MVTB_UNROLL
@@ -691,7 +668,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             }
         }
     }
-    __syncthreads(); MVTB_MIDW_STAMP(1);
+    __syncthreads();
 
     // ---- D axis forward, pair-folded like the other axes: with e = G[d] + G[D-d], o = G[d] - G[D-d] (in place),
     //   B(+-fd) = G[0] (+ G[D/2] (-1)^fd) + P -+ iQ,   P = sum_d e cos(2 pi fd d / D),  Q = sum_d o sin(2 pi fd d / D)
@@ -739,7 +716,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             }
         }
     }
-    __syncthreads(); MVTB_MIDW_STAMP(2);
+    __syncthreads();
     // E = B(+fd) + B(-fd), O = B(+fd) - B(-fd) packed as float4 over the now free G tile: the way back along D is
     //   G'[j][d] = B(0) + sum_fd ( E cos(2 pi fd d / D) + i O sin(2 pi fd d / D) )
     float4* seo = (float4*)sg;                            // [K][F + 1]; entry 0 of a row holds (B(0), 0)
@@ -750,7 +727,7 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
     }
     __syncthreads();
     bl_load_table<NF>(sc, g.tabC[1], g.tabS[1], W, tid, nthr);      // over the bins, which are no longer needed
-    __syncthreads(); MVTB_MIDW_STAMP(3);
+    __syncthreads();
 
     // ---- back along D (into registers) and along W (streamed out in place)
     for (int d = tid; d < D; d += nthr) {
@@ -820,5 +797,4 @@ k_bl_midw(cf* __restrict__ Y, BlGeom g, const BlVol* __restrict__ vols, int vol_
             yv[(size_t)(W - w) * D] = cmk(Px + Qy, Py - Qx);
         }
     }
-    MVTB_MIDW_STAMP(4);
 }
