@@ -55,7 +55,7 @@ WORKLOADS = {
                   channels=4, batch=256, strong_total=256, r=12.5, spike=False, alpha=None, p=0.15),
 }
 # configs[3] and configs[4] of BASELINE.json have other units of work (2-D slices; 128x128x64 crops): bench.py --workload cfg4|cfg5
-AUX_WORKLOADS = ("cfg4", "cfg5")
+AUX_WORKLOADS = ("cfg4", "cfg5", "train127")
 
 
 def peak_hbm():
@@ -309,6 +309,44 @@ def run_aux_workload(args):
         step = lambda: t4(x)                                              # noqa: E731
         units, unit, voxels, metric = 8192, "slices/s", x.numel(), "slices/sec (240x240 fp32)"
         name = "cfg4: KSpaceSpikeNoise 2-D, one location for (8192,240,240) (F:982-983)"
+    elif args.workload == "train127":
+        # The 127 scripts' per-sample training transform from the resampled volume on (127_...FLAIR.py:130-141), at the
+        # scripts' own shapes: (1, 160, 160, 78) after Spacingd(1.5, 1.5, 2.0) -> RandSpatialCropd(128,128,64) -> RandFlipd ->
+        # NormalizeIntensityd / RandScale / RandShift (one statistics pass; the map rides on the chain's forward kernel)
+        # -> disk 12.5 -> plane-wave spike -> wrap 0.5 -> S&P 0.05, for a batch of 64 samples
+        import ctypes as C
+        from mvtb import host
+        B = 64
+        src = torch.randn(B, 1, 160, 160, 78, device=dev, generator=g).abs_()
+        src *= (src > 0.3)                                                # zero background
+        R = np.random.RandomState(99 + rank)
+        starts = [(int(R.randint(0, 33)), int(R.randint(0, 33)), int(R.randint(0, 15))) for _ in range(B)]
+        flips = [int(R.rand() < 0.5) for _ in range(B)]
+        scales = torch.tensor([1.0 + R.uniform(-0.1, 0.1) for _ in range(B)], dtype=torch.float32)
+        shifts = torch.tensor([R.uniform(-0.1, 0.1) for _ in range(B)], dtype=torch.float32)
+        shell = host.ellipsoid_shell((128, 128, 64), 55., 55., 30.)
+        idxs = [tuple(int(v) for v in shell[R.randint(0, len(shell))]) for _ in range(B)]
+        thr = host.disk_threshold(12.5, (128, 128, 64))
+        descs = host.desc_array([host.make_desc(mask_kind=_lib.MASK_DISK, mask_ndim=3, mask_thresh=thr, spikes=[(i, host.exp_f32(15.0))], wrap_alpha=0.5)
+                                 for i in idxs])
+        xc = torch.empty(B, 1, 128, 128, 64, device=dev)
+        yo = torch.empty_like(xc)
+        i3 = C.c_int32 * 3
+        stream = Fn._stream(dev)
+
+        st_dev = torch.tensor(starts, dtype=torch.int32, device=dev)
+        fl_dev = torch.tensor(flips, dtype=torch.int32, device=dev)
+
+        def step():
+            # crop + flip: one gather for the batch (the windows and flips were drawn on the host, as the loader does)
+            _lib.check(L, L.mvtb_crop_flip_batch_f32(Fn._ptr(src), Fn._ptr(xc), B, 1, i3(160, 160, 78), i3(128, 128, 64), Fn._ptr(st_dev),
+                                                     Fn._ptr(fl_dev), stream))
+            abt = Fn.intensity_coeffs(xc, B, scale=scales, shift=shifts)  # one read of the crops
+            return Fn.kspace_chain_ex(xc, 3, descs, pre_abt=abt, sp=(0.05, 7, 0), out=yo)[0]
+
+        units, unit, voxels, metric = B, "volumes/s", xc.numel() * 20 / 8, "volumes/sec (train transform, 128x128x64 fp32)"
+        name = ("train127: crop + flip (8 B/voxel) -> intensity statistics (4) -> chain-127 with the intensity map applied on load and the "
+                "select pass (8) on (64,1,128,128,64) crops of (64,1,160,160,78) volumes = 20 B/voxel")
     else:
         B = 32
         x = torch.randn(B, 1, 128, 128, 64, device=dev, generator=g)
@@ -343,7 +381,7 @@ def run_aux_workload(args):
                           "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "f32", "data": "synthetic", "config": {"workload": name, "l2": "flushed between steps (256 MB written)"},
                           "roofline_whole_step": {"achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
-                                                  "note": "8 B/voxel per transform"},
+                                                  "note": "20 B per output voxel (see config.workload)" if args.workload == "train127" else "8 B/voxel per transform"},
                           "gpu_launches": launches}), flush=True)
     if world > 1:
         dist.barrier()

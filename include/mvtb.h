@@ -196,6 +196,10 @@ int mvtb_sqdiff_sum_f32(const float* a, const float* b, size_t n, double* sum_ou
  * spatial axis a reversed (np.flip after the crop).  The host draws offsets and flips in MONAI's order. in != out. */
 int mvtb_crop_flip_f32(const float* in, float* out, int n_channels, const int32_t* in_shape, const int32_t* out_shape,
                        const int32_t* offset, int flip_axes_mask, void* stream);
+/* the same for n_samples samples of one shape in one launch, each with its own window and flips: offsets_dev[3 n_samples] and
+ * flips_dev[n_samples] are int32 arrays ON THE DEVICE (windows are not range-checked). */
+int mvtb_crop_flip_batch_f32(const float* in, float* out, int n_samples, int n_channels, const int32_t* in_shape,
+                             const int32_t* out_shape, const int32_t* offsets_dev, const int32_t* flips_dev, void* stream);
 
 /* WrapArtifact (F:503-515) on (C,H,W,D) when H, W and D are all even: the image-domain fold
  * out = prod_axes (c0 + s c1 Roll_{N/2}) x, c0=(1+alpha)/2, c1=(1-alpha)/2, s=(-1)^(N/2)

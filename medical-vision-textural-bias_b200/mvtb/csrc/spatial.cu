@@ -40,6 +40,32 @@ k_crop_flip(const float* __restrict__ in, float* __restrict__ out, CropGeom g, l
     }
 }
 
+// the same gather for a batch of samples of one shape, each with its own window and flips (device arrays: the training
+// loader draws them per sample); sample b reads in + b * in_sample, writes out + b * (C s0 s1 s2)
+__global__ void __launch_bounds__(256)
+k_crop_flip_batch(const float* __restrict__ in, float* __restrict__ out, CropGeom g, long long rows_per_sample, long long in_sample,
+                  const int* __restrict__ offsets, const int* __restrict__ flips, long long n_rows_total) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nw = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long rr = wid; rr < n_rows_total; rr += nw) {
+        const long long b = rr / rows_per_sample, r = rr - b * rows_per_sample;
+        const int o0 = __ldg(offsets + 3 * b), o1 = __ldg(offsets + 3 * b + 1), o2 = __ldg(offsets + 3 * b + 2), fl = __ldg(flips + b);
+        const long long c = r / ((long long)g.s0 * g.s1);
+        const int rem = (int)(r - c * (long long)g.s0 * g.s1);
+        const int i = rem / g.s1, j = rem - i * g.s1;
+        const int si = o0 + ((fl & 1) ? g.s0 - 1 - i : i);
+        const int sj = o1 + ((fl & 2) ? g.s1 - 1 - j : j);
+        const float* src = in + b * in_sample + c * g.in_chan + ((long long)si * g.iw + sj) * g.id + o2;
+        float* dst = out + rr * g.s2;
+        if (fl & 4) {
+            for (int k = lane; k < g.s2; k += 32) dst[k] = src[g.s2 - 1 - k];
+        } else {
+            for (int k = lane; k < g.s2; k += 32) dst[k] = src[k];
+        }
+    }
+}
+
 }  // namespace mvtb
 
 using namespace mvtb;
@@ -66,6 +92,31 @@ extern "C" int mvtb_crop_flip_f32(const float* in, float* out, int n_channels, c
     long long blocks = (rows + 7) / 8;                      // 8 warps per CTA
     if (blocks > 148 * 16) blocks = 148 * 16;
     MVTB_LAUNCH(k_crop_flip, dim3((unsigned)blocks), dim3(256), 0, stream, in, out, g, rows);
+    MVTB_CUDA(cudaGetLastError());
+    return MVTB_OK;
+}
+
+// offsets_dev[3 n_samples], flips_dev[n_samples]: int32 on the device; every window must fit (the caller draws them with
+// MONAI's bounds, 0 <= o <= N - s); not checked here, the arrays live on the device.
+extern "C" int mvtb_crop_flip_batch_f32(const float* in, float* out, int n_samples, int n_channels, const int32_t* in_shape,
+                                        const int32_t* out_shape, const int32_t* offsets_dev, const int32_t* flips_dev, void* stream) {
+    if (!in || !out || !in_shape || !out_shape || !offsets_dev || !flips_dev) { set_error("crop_flip_batch: null argument"); return MVTB_EINVAL; }
+    if (in == out) { set_error("crop_flip_batch: in-place is not supported"); return MVTB_EINVAL; }
+    if (n_samples < 0 || n_channels < 0) { set_error("crop_flip_batch: negative count"); return MVTB_EINVAL; }
+    for (int a = 0; a < 3; ++a)
+        if (in_shape[a] < 1 || out_shape[a] < 0 || out_shape[a] > in_shape[a]) { set_error("crop_flip_batch: axis %d: size %d of %d", a, out_shape[a], in_shape[a]); return MVTB_EINVAL; }
+    const long long rows_per_sample = (long long)n_channels * out_shape[0] * out_shape[1];
+    const long long rows = rows_per_sample * n_samples;
+    if (rows == 0 || out_shape[2] == 0) return MVTB_OK;
+    CropGeom g;
+    g.iw = in_shape[1]; g.id = in_shape[2];
+    g.in_chan = (long long)in_shape[0] * in_shape[1] * in_shape[2];
+    g.s0 = out_shape[0]; g.s1 = out_shape[1]; g.s2 = out_shape[2];
+    g.o0 = g.o1 = g.o2 = 0; g.flip = 0;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    MVTB_LAUNCH(k_crop_flip_batch, dim3((unsigned)blocks), dim3(256), 0, stream, in, out, g, rows_per_sample, g.in_chan * n_channels,
+                offsets_dev, flips_dev, rows);
     MVTB_CUDA(cudaGetLastError());
     return MVTB_OK;
 }

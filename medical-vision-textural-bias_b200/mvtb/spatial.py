@@ -62,6 +62,28 @@ def crop_flip(x, start: Sequence[int], size: Sequence[int], flip_axes_mask: int 
     return Fn.back(out, org)
 
 
+def crop_flip_batch(x: torch.Tensor, starts, size: Sequence[int], flip_masks) -> torch.Tensor:
+    """out[b] = flip_b(x[b, :, start_b : start_b + size]) for a CUDA batch (B, C, H, W, D) in one launch; starts: (B, 3) ints,
+    flip_masks: (B,) ints (bit a = spatial axis a), as tensors or sequences."""
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 5:
+        raise ValueError("crop_flip_batch expects a contiguous float32 CUDA tensor (B, C, H, W, D)")
+    B_, C_ = int(x.shape[0]), int(x.shape[1])
+    st = torch.as_tensor(starts, dtype=torch.int32).reshape(B_, 3)
+    fm = torch.as_tensor(flip_masks, dtype=torch.int32).reshape(B_)
+    sz = tuple(int(v) for v in size)
+    if bool((st < 0).any()) or any(int(st[:, a].max()) + sz[a] > int(x.shape[2 + a]) for a in range(3)):
+        raise ValueError("crop_flip_batch: a window does not fit in the volume")
+    st, fm = st.to(x.device), fm.to(x.device)
+    out = torch.empty((B_, C_) + sz, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    i3 = C.c_int32 * 3
+    with torch.cuda.device(x.device):
+        rc = L.mvtb_crop_flip_batch_f32(Fn._ptr(x), Fn._ptr(out), B_, C_, i3(*[int(v) for v in x.shape[2:]]), i3(*sz), Fn._ptr(st), Fn._ptr(fm),
+                                        Fn._stream(x.device))
+    _lib.check(L, rc)
+    return out
+
+
 def _center_start(img_size: Sequence[int], roi: Sequence[int]):
     """CenterSpatialCrop -> SpatialCrop(roi_center=[i // 2], roi_size): start = max(center - roi // 2, 0), clipped at the end"""
     start = [max(n // 2 - r // 2, 0) for n, r in zip(img_size, roi)]

@@ -117,3 +117,16 @@ def test_gpu_dropins_follow_monai_draw_order(cuda_device):
     R = np.random.RandomState(5)
     sl = M.rand_spatial_crop_slices((40, 36, 31), [16, 20, 12], R, random_size=True)
     assert torch.equal(o["image"].cpu(), torch.from_numpy(np.ascontiguousarray(img.numpy()[(slice(None),) + sl])))
+
+
+@pytest.mark.gpu
+def test_gpu_batched_gather(cuda_device):
+    from mvtb import spatial as S
+    x = torch.stack([P.synthetic_volume(20 + b, (2, 20, 18, 37)) for b in range(5)])
+    starts = [(0, 0, 0), (4, 2, 5), (7, 0, 1), (1, 3, 0), (8, 6, 5)]
+    masks = [0, 1, 6, 7, 4]
+    got = S.crop_flip_batch(x.to(cuda_device), starts, (12, 12, 32), masks)
+    for b in range(5):
+        assert torch.equal(got[b].cpu(), torch.from_numpy(_want(x[b].numpy(), (12, 12, 32), starts[b], masks[b])))
+    with pytest.raises(ValueError):
+        S.crop_flip_batch(x.to(cuda_device), [(9, 0, 0)] * 5, (12, 12, 32), masks)
