@@ -1016,8 +1016,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         if (tc_ring > kTcMaxRing) tc_ring = kTcMaxRing;
         if (tc_slots > 0) tc_ring -= tc_ring % tc_slots;          // a multiple of the converter groups (= slots): see the kernel
         const size_t smem_tc = tc_tab + (size_t)tc_ring * tc_bs * kTcRows * 128 * sizeof(float);
-        // (with an intensity prologue the cp.async FFMA kernel applies the map as it reads: one pass instead of two)
-        tc_fwd = p->opt_tc && (pre_abt == nullptr || p->opt_tc_inv) && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
+        tc_fwd = p->opt_tc && (g.H % kTcRows) == 0 && (g.NC % 4) == 0 && ((((uintptr_t)in) & 15) == 0) && tcN <= 64 &&
                  tc_ring >= 2 && tc_slots >= 2 && g.NC * (long long)g.H < 0x7fffffffLL;
 #endif
         {
@@ -1028,12 +1027,6 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 // pruned DFT along H as a 3xTF32 GEMM on the tensor cores (bandlimited_tc.cuh)
                 TcFwdArgs ta;
                 CUtensorMap tmap;
-                if (abt_v) {
-                    int rca = mvtb_intensity_affine_f32(src, out + (size_t)v0 * p->vol_real, p->vol_real, nv, abt_v, stream);
-                    if (rca != MVTB_OK) return rca;
-                    src = out + (size_t)v0 * p->vol_real;
-                    abt_v = nullptr;
-                }
                 int rcm = tc_make_tmap(&tmap, src, (unsigned long long)nv * g.H, (unsigned long long)g.NC, 128, tc_bs * kTcRows);
                 if (rcm != MVTB_OK) return rcm;
                 ta.Y = Y;
@@ -1045,6 +1038,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 ta.box_stages = tc_bs;
                 ta.ring_boxes = tc_ring;
                 ta.a_slots = tc_slots;
+                ta.abt = abt_v;                                // the intensity prologue map, applied as the converters read x
                 ta.status = p->tc_status;
                 ta.prof = nullptr;
                 if (getenv("MVTB_TC_PROF")) {                  // measurements: waits and an event timeline of CTA 0, printed at the next call

@@ -39,6 +39,8 @@ struct TcFwdArgs {
     int box_stages;          // stages (of 16 rows) per TMA box and per A-operand slot
     int ring_boxes;          // boxes in the raw shared-memory ring
     int a_slots;             // A-operand slots in TMEM (each 32 * box_stages columns)
+    const float* abt;        // null, or the intensity prologue map of every volume of the launch (a, b, t): y = x != 0 ? a x + b : t,
+                             // applied by the converters as they read x (mvtb_kspace_chain_ex_f32, pre_abt)
     int* status;
     long long* prof;         // null, or wait cycles / event timeline of CTA 0 (MVTB_TC_PROF)
 };
@@ -242,10 +244,19 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
             tc::fence_after_sync();
             const float* rp = raw + (size_t)rb * box_floats + m;
             const uint32_t t0 = tmem + ((uint32_t)(32 * q) << 16) + a_col0 + (uint32_t)sl * slot_cols;
+            float pa = 1.f, pb = 0.f, pt = 0.f;
+            if (a.abt != nullptr) {                                       // the box's volume: tile = blockIdx.x + (ib / n_box) gridDim.x
+                const int vol = (int)((blockIdx.x + (ib / (unsigned)n_box) * gridDim.x) / (unsigned)a.tiles_per_vol);
+                pa = __ldg(a.abt + 3 * vol); pb = __ldg(a.abt + 3 * vol + 1); pt = __ldg(a.abt + 3 * vol + 2);
+            }
             for (int k = 0; k < bs; ++k) {
                 float v[kTcRows];
                 MVTB_UNROLL
                 for (int j = 0; j < kTcRows; ++j) v[j] = rp[(k * kTcRows + j) * 128];
+                if (a.abt != nullptr) {
+                    MVTB_UNROLL
+                    for (int j = 0; j < kTcRows; ++j) v[j] = v[j] != 0.f ? fmaf(pa, v[j], pb) : pt;
+                }
                 uint32_t hi[kTcRows], lo[kTcRows];
                 MVTB_UNROLL
                 for (int j = 0; j < kTcRows; ++j) {

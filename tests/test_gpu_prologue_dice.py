@@ -69,7 +69,7 @@ def test_chain_applies_prologue_on_load(cuda_device):
     ms, cn = (C.c_double * _lib.K_KINDS)(), (C.c_int * _lib.K_KINDS)()
     _lib.check(L, L.mvtb_plan_profile_read(plan, ms, cn))
     _lib.check(L, L.mvtb_plan_profile(plan, 0))
-    assert cn[5] == 1                                     # k_bl_fwd_h: the map rode on the forward kernel, no extra pass
+    assert cn[5] + cn[14] == 1                            # k_bl_fwd_h / k_bl_fwd_tc: the map rode on the forward kernel, no extra pass
     assert rel_l2(got3.cpu().numpy(), want3.cpu().numpy()) <= 2e-6
     want4, _ = Fn.kspace_chain_sp(xa, 3, descs, 0.05, seed=3, offset=0)
     got4, mm = Fn.kspace_chain_ex(x, 3, descs, pre_abt=abt, sp=(0.05, 3, 0))
