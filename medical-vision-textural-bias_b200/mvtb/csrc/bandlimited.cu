@@ -1006,10 +1006,16 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
         // TMA boxes / A-operand slots of k stages of 16 rows, k the largest divisor of H / 16 up to kTcMaxBoxStages whose
         // slots (32 k TMEM columns each, at least two) fit beside the six accumulators; the raw ring takes what shared
         // memory is left next to the table, at most kTcMaxRing boxes
-        int tc_bs = 1, tc_slots = 0;
+        int tc_bs = 1, tc_slots = 0, tc_sets = 2;
         for (int k = 1; k <= kTcMaxBoxStages; ++k)
             if ((g.H / kTcRows) % k == 0 && 6 * tcN + 2 * 32 * k <= 512) tc_bs = k;
-        tc_slots = (512 - 6 * tcN) / (32 * tc_bs);
+        if (tc_bs == 1 && g.H / kTcRows > 1) {                  // six accumulators would leave single-stage slots: one set of three
+            int k1 = 1;
+            for (int k = 1; k <= kTcMaxBoxStages; ++k)
+                if ((g.H / kTcRows) % k == 0 && 3 * tcN + 2 * 32 * k <= 512) k1 = k;
+            if (k1 > 1) { tc_sets = 1; tc_bs = k1; }
+        }
+        tc_slots = (512 - 3 * tc_sets * tcN) / (32 * tc_bs);
         if (tc_slots > kTcMaxSlots) tc_slots = kTcMaxSlots;
         const size_t tc_tab = ((size_t)2 * g.H * tcN * sizeof(float) + 1023) & ~(size_t)1023;
         int tc_ring = (int)(((size_t)220 * 1024 - tc_tab) / ((size_t)tc_bs * kTcRows * 128 * sizeof(float)));
@@ -1038,6 +1044,7 @@ static int bl_run(mvtb_plan* p, const float* in, float* out, int n_volumes, cons
                 ta.box_stages = tc_bs;
                 ta.ring_boxes = tc_ring;
                 ta.a_slots = tc_slots;
+                ta.acc_sets = tc_sets;
                 ta.abt = abt_v;                                // the intensity prologue map, applied as the converters read x
                 ta.status = p->tc_status;
                 ta.prof = nullptr;

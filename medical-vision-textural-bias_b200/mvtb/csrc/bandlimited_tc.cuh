@@ -39,6 +39,8 @@ struct TcFwdArgs {
     int box_stages;          // stages (of 16 rows) per TMA box and per A-operand slot
     int ring_boxes;          // boxes in the raw shared-memory ring
     int a_slots;             // A-operand slots in TMEM (each 32 * box_stages columns)
+    int acc_sets;            // 2: the accumulators of even / odd tiles are separate (6 N TMEM columns); 1: one set of three (3 N),
+                             // for N = 64 (NF = 26, 32), where six would leave room for single-stage slots only
     const float* abt;        // null, or the intensity prologue map of every volume of the launch (a, b, t): y = x != 0 ? a x + b : t,
                              // applied by the converters as they read x (mvtb_kspace_chain_ex_f32, pre_abt)
     int* status;
@@ -153,10 +155,11 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
         const uint32_t chunk_stride = (uint32_t)(N / 8) * 128u, group_stride = 128u;
         const uint32_t b0 = tc::smem_u32(term == 2 ? tab_lo : tab_hi);
         const uint32_t a_off = term == 1 ? 16u : 0u;                         // within a stage's 32 columns: [hi 16 | lo 16]
-        const uint32_t d = tmem + d_col0 + (uint32_t)iss * (uint32_t)N;
+        const uint32_t d = tmem + d_col0 + (uint32_t)(a.acc_sets == 2 ? iss : term) * (uint32_t)N;
+        const bool two = a.acc_sets == 2;
         unsigned ib = 0, tcount = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles && !*abortp; tile += gridDim.x, ++tcount) {
-            if ((int)(tcount & 1u) != set) {
+            if (two ? (int)(tcount & 1u) != set : set != 0) {
                 // The other set's tile.  Still observe every fill and sign the slot off: a parity wait is only sound
                 // when the waiter is never a phase ahead of or behind its barrier, so all six issuers see all boxes.
                 bool ok = true;
@@ -169,7 +172,7 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
                 if (!ok) break;
                 continue;
             }
-            if (!tc_wait(&bars.d_empty[set], ((tcount >> 1) & 1u) ^ 1u, abortp, a.status, 2, a.prof)) break;
+            if (!tc_wait(&bars.d_empty[set], (((two ? tcount >> 1 : tcount)) & 1u) ^ 1u, abortp, a.status, 2, a.prof)) break;
             tc::fence_after_sync();
             uint32_t acc = 0;
             bool ok = true;
@@ -200,8 +203,8 @@ k_bl_fwd_tc(const __grid_constant__ CUtensorMap tmap, TcFwdArgs a) {
         unsigned tcount = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles && !*abortp; tile += gridDim.x, ++tcount) {
             const int vol = tile / a.tiles_per_vol, c0 = (tile - vol * a.tiles_per_vol) * 128;
-            const unsigned set = tcount & 1u;
-            if (!tc_wait(&bars.d_full[set], (tcount >> 1) & 1u, abortp, a.status, 4, a.prof)) break;
+            const unsigned set = a.acc_sets == 2 ? tcount & 1u : 0u;
+            if (!tc_wait(&bars.d_full[set], (a.acc_sets == 2 ? tcount >> 1 : tcount) & 1u, abortp, a.status, 4, a.prof)) break;
             tc::fence_after_sync();
             const bool okc = c0 + m < NC;
             float2* yv = a.Y + ((size_t)vol * a.NF) * NC + c0 + m;
